@@ -1,0 +1,35 @@
+"""b200-blockdct: B200-native 8x8 block DCT -> quantise -> IDCT (drop-in for the hot path
+of GerryDps/CUDA-DCT-IDCT).
+
+The product is the CUDA library built from ``csrc/`` (``libb200dct.so``: the C ABI of
+``include/b200dct.h``; ``libb200dct_compat.so``: the reference's own C++ entry points).
+This package is only the thin Python host side over that C ABI: ctypes bindings that
+take torch CUDA tensors (device memory, streams) or numpy host arrays.  There is no
+CPU fallback -- importing works anywhere, computing requires the built library and a GPU.
+"""
+from .api import (  # noqa: F401
+    ALL_COEFFS,
+    B200DCTError,
+    Plan,
+    dct_all_blocks,
+    dct_all_blocks_cuda,
+    forward,
+    idct_all_blocks,
+    idct_all_blocks_cuda,
+    inverse,
+    lib,
+    lib_path,
+    metrics,
+    roundtrip,
+    roundtrip_host,
+    zigzag_mask,
+)
+from . import api, dist  # noqa: F401
+from .build import build  # noqa: F401
+from .stripes import stripe_rows  # noqa: F401
+
+__all__ = [
+    "ALL_COEFFS", "B200DCTError", "Plan", "build", "dct_all_blocks", "dct_all_blocks_cuda", "forward",
+    "idct_all_blocks", "idct_all_blocks_cuda", "inverse", "lib", "lib_path", "metrics", "roundtrip",
+    "roundtrip_host", "stripe_rows", "zigzag_mask",
+]

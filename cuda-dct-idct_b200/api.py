@@ -1,0 +1,323 @@
+"""ctypes host side over the C ABI (include/b200dct.h) and the compat library.
+
+Tensors are torch CUDA tensors (torch is used only for device memory and streams) for the
+device entry points, numpy arrays for the host-buffer round trip.  The functions named
+like the reference's (``dct_all_blocks_cuda`` ...) keep its argument order
+``(image, H, W, T, result)`` -- height before width (main_newAppr.cu:23-24) -- and its side
+effects, by calling the same compiled wrappers a C++ caller would link.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ALL_COEFFS = (1 << 64) - 1
+
+F32, U8, I16 = 0, 1, 2
+PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
+
+
+class B200DCTError(RuntimeError):
+    pass
+
+
+def lib_path(name: str = "libb200dct.so") -> str:
+    return os.path.join(_HERE, name)
+
+
+_lib = None
+_compat = None
+
+
+def lib() -> C.CDLL:
+    """Load libb200dct.so.  Fails loudly if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        p = lib_path()
+        if not os.path.exists(p):
+            raise B200DCTError(
+                f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+        L = C.CDLL(p)
+        vp, sz, i, u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+        L.b200dct_plan_create.argtypes = [C.POINTER(vp)]
+        L.b200dct_plan_destroy.argtypes = [vp]
+        L.b200dct_plan_destroy.restype = None
+        L.b200dct_plan_set_quant.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b200dct_plan_get_quant.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b200dct_plan_set_transform.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b200dct_plan_set_transform_device.argtypes = [vp, vp]
+        L.b200dct_plan_set_keep_mask.argtypes = [vp, u64]
+        L.b200dct_zigzag_mask.argtypes = [i]
+        L.b200dct_zigzag_mask.restype = u64
+        L.b200dct_plan_set_path.argtypes = [vp, i]
+        L.b200dct_plan_is_sparse.argtypes = [vp]
+        L.b200dct_forward.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, i, vp]
+        L.b200dct_inverse.argtypes = [vp, vp, i, sz, vp, i, sz, i, i, vp]
+        L.b200dct_roundtrip.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp]
+        L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
+        L.b200dct_metrics_accumulate.argtypes = [vp, vp, i, sz, i, i, vp, vp]
+        L.b200dct_selftest_division.argtypes = [C.c_float, C.c_ulonglong, C.c_ulonglong, vp, vp]
+        L.b200dct_last_launch_count.restype = i
+        L.b200dct_last_path.restype = C.c_char_p
+        L.b200dct_error_string.argtypes = [i]
+        L.b200dct_error_string.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def compat_lib() -> C.CDLL:
+    global _compat
+    if _compat is None:
+        lib()  # dependency, and the loud failure
+        L = C.CDLL(lib_path("libb200dct_compat.so"))
+        vp, i = C.c_void_p, C.c_int
+        L.b200dct_compat_set_quant.argtypes = [C.POINTER(C.c_float)]
+        L.b200dct_compat_set_keep_mask.argtypes = [C.c_uint64]
+        L.b200dct_compat_set_options.argtypes = [i, i]
+        L.b200dct_compat_set_options.restype = None
+        L.b200dct_compat_last_ms.restype = C.c_float
+        for f in (L.b200dct_compat_dct, L.b200dct_compat_idct, L.b200dct_compat_idct_inplace_dequant):
+            f.argtypes = [vp, i, i, vp, vp]
+            f.restype = None
+        _compat = L
+    return _compat
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise B200DCTError(f"b200dct error {rc}: {lib().b200dct_error_string(rc).decode()}")
+
+
+def zigzag_mask(k: int) -> int:
+    return int(lib().b200dct_zigzag_mask(int(k)))
+
+
+def _f64(a) -> "C.Array":
+    a = np.ascontiguousarray(a, np.float32).reshape(64)
+    return (C.c_float * 64)(*a.tolist())
+
+
+class Plan:
+    """T, Q and the retained-coefficient mask (b200dct_plan)."""
+
+    def __init__(self, T=None, Q=None, keep: int = ALL_COEFFS, path: int = PATH_AUTO):
+        self._h = C.c_void_p()
+        _check(lib().b200dct_plan_create(C.byref(self._h)))
+        if T is not None:
+            self.set_transform(T)
+        if Q is not None:
+            self.set_quant(Q)
+        if keep != ALL_COEFFS:
+            self.set_keep_mask(keep)
+        if path != PATH_AUTO:
+            self.set_path(path)
+
+    def set_transform(self, T) -> None:
+        _check(lib().b200dct_plan_set_transform(self._h, _f64(T)))
+
+    def set_quant(self, Q) -> None:
+        _check(lib().b200dct_plan_set_quant(self._h, _f64(Q)))
+
+    def quant(self) -> np.ndarray:
+        q = (C.c_float * 64)()
+        _check(lib().b200dct_plan_get_quant(self._h, q))
+        return np.array(q[:], np.float32)
+
+    def set_keep_mask(self, mask: int) -> None:
+        _check(lib().b200dct_plan_set_keep_mask(self._h, mask & ALL_COEFFS))
+
+    def set_path(self, path: int) -> None:
+        _check(lib().b200dct_plan_set_path(self._h, path))
+
+    @property
+    def is_sparse(self) -> bool:
+        return bool(lib().b200dct_plan_is_sparse(self._h))
+
+    def __del__(self):
+        try:
+            if self._h and _lib is not None:
+                _lib.b200dct_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+_default_plan = None
+
+
+def _plan(plan):
+    global _default_plan
+    if plan is not None:
+        return plan
+    if _default_plan is None:
+        _default_plan = Plan()
+    return _default_plan
+
+
+def _dt(t) -> int:
+    import torch
+
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.uint8:
+        return U8
+    if t.dtype == torch.int16:
+        return I16
+    raise B200DCTError(f"unsupported dtype {t.dtype}")
+
+
+def _plane(t):
+    """(ptr, dtype code, pitch bytes, H, W) of a 2-d (or batch-as-rows 3-d) CUDA tensor."""
+    if not t.is_cuda:
+        raise B200DCTError("device entry points take CUDA tensors (no CPU path)")
+    if t.dim() == 3:  # B x H x W stored back to back == one (B*H) x W image
+        if not t.is_contiguous():
+            raise B200DCTError("batched tensors must be contiguous")
+        t = t.view(-1, t.shape[-1])
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise B200DCTError("expected a row-major 2-d tensor")
+    return t.data_ptr(), _dt(t), t.stride(0) * t.element_size(), t.shape[0], t.shape[1]
+
+
+def _stream(stream):
+    import torch
+
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def forward(img, coef=None, plan: Plan | None = None, coef_dtype=None, shifted=None, stream=None):
+    """coef = round(T.(img-128).T^T / Q); img f32|u8 CUDA tensor; coef f32 (default) or int16."""
+    import torch
+
+    ip, idt, ipitch, H, W = _plane(img)
+    if coef is None:
+        coef = torch.empty(img.shape, dtype=coef_dtype or torch.float32, device=img.device)
+    cp, cdt, cpitch, _, _ = _plane(coef)
+    sp = _plane(shifted)[0] if shifted is not None else None
+    with torch.cuda.device(img.device):
+        _check(lib().b200dct_forward(_plan(plan)._h, ip, idt, ipitch, cp, cdt, cpitch, sp, H, W, _stream(stream)))
+    return coef
+
+
+def inverse(coef, img=None, plan: Plan | None = None, img_dtype=None, stream=None):
+    """img = T^T.(coef*Q).T + 128; coef f32|int16; img f32 (unclamped) or u8 (clamp+truncate)."""
+    import torch
+
+    cp, cdt, cpitch, H, W = _plane(coef)
+    if img is None:
+        img = torch.empty(coef.shape, dtype=img_dtype or torch.float32, device=coef.device)
+    ip, idt, ipitch, _, _ = _plane(img)
+    with torch.cuda.device(coef.device):
+        _check(lib().b200dct_inverse(_plan(plan)._h, cp, cdt, cpitch, ip, idt, ipitch, H, W, _stream(stream)))
+    return img
+
+
+def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None):
+    """Fused DCT -> quantise -> dequantise -> IDCT in one pass; optional coefficient plane."""
+    import torch
+
+    ip, idt, ipitch, H, W = _plane(img)
+    if out is None:
+        out = torch.empty_like(img)
+    op, odt, opitch, _, _ = _plane(out)
+    if coef is not None:
+        cp, cdt, cpitch, _, _ = _plane(coef)
+    else:
+        cp, cdt, cpitch = None, F32, 0
+    with torch.cuda.device(img.device):
+        _check(lib().b200dct_roundtrip(_plan(plan)._h, ip, idt, ipitch, op, odt, opitch, cp, cdt, cpitch, H, W,
+                                       _stream(stream)))
+    return out
+
+
+def roundtrip_host(h_in, h_out=None, plan: Plan | None = None):
+    """Host buffers in, host buffers out (numpy arrays or pinned CPU torch tensors):
+    chunked H2D -> fused kernel -> D2H pipeline inside the library.  Synchronous."""
+    import torch
+
+    def hostptr(a):
+        if isinstance(a, np.ndarray):
+            if not a.flags.c_contiguous:
+                raise B200DCTError("host arrays must be C-contiguous")
+            dt = {np.dtype(np.float32): F32, np.dtype(np.uint8): U8}.get(a.dtype)
+            return a.ctypes.data, dt, a.shape
+        if isinstance(a, torch.Tensor) and not a.is_cuda and a.is_contiguous():
+            return a.data_ptr(), _dt(a), tuple(a.shape)
+        raise B200DCTError("expected a contiguous numpy array or CPU torch tensor")
+
+    ip, idt, shape = hostptr(h_in)
+    if idt is None or idt == I16:
+        raise B200DCTError("host round trip takes float32 or uint8 pixels")
+    if h_out is None:
+        h_out = np.empty_like(h_in) if isinstance(h_in, np.ndarray) else torch.empty_like(h_in)
+    op, odt, oshape = hostptr(h_out)
+    if oshape != shape:
+        raise B200DCTError("shape mismatch")
+    H = int(np.prod(shape[:-1]))
+    _check(lib().b200dct_roundtrip_host(_plan(plan)._h, ip, idt, op, odt, H, int(shape[-1])))
+    return h_out
+
+
+def metrics(ref_img, test_img, stream=None):
+    """(MSE, PEEN%) of test_img against ref_img, accumulated on the device in double."""
+    import torch
+
+    rp, rdt, rpitch, H, W = _plane(ref_img)
+    tp, tdt, tpitch, _, _ = _plane(test_img)
+    if rdt != tdt or rpitch != tpitch:
+        raise B200DCTError("metrics needs two images of the same dtype and pitch")
+    acc = torch.zeros(2, dtype=torch.float64, device=ref_img.device)
+    with torch.cuda.device(ref_img.device):
+        _check(lib().b200dct_metrics_accumulate(rp, tp, rdt, rpitch, H, W, acc.data_ptr(), _stream(stream)))
+    sse, energy = acc.tolist()
+    n = H * W
+    return sse / n, (100.0 * (sse / energy) ** 0.5 if energy > 0 else 0.0)
+
+
+def last_launch_count() -> int:
+    return int(lib().b200dct_last_launch_count())
+
+
+def last_path() -> str:
+    return lib().b200dct_last_path().decode()
+
+
+# ---------------------------------------------------------------- reference-named entry points
+def _compat_call(fn, a, H, W, T, result):
+    import torch
+
+    for t in (a, T, result):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise B200DCTError("the reference's entry points take contiguous float32 device buffers")
+    if a.numel() < H * W or result.numel() < H * W or T.numel() < 64:
+        raise B200DCTError("buffer smaller than H*W")
+    with torch.cuda.device(a.device):
+        torch.cuda.current_stream().synchronize()  # the wrappers run on the legacy default stream
+        fn(a.data_ptr(), int(H), int(W), T.data_ptr(), result.data_ptr())
+
+
+def dct_all_blocks_cuda(image_matrix, img_height, img_width, transform_matrix, result):
+    """main_newAppr.cu:252 / main_fastAppr.cu:303.  Leaves image_matrix holding image-128."""
+    _compat_call(compat_lib().b200dct_compat_dct, image_matrix, img_height, img_width, transform_matrix, result)
+
+
+def idct_all_blocks_cuda(image_matrix, img_height, img_width, transform_matrix, result):
+    """main_newAppr.cu:293 / main_fastAppr.cu:361."""
+    _compat_call(compat_lib().b200dct_compat_idct, image_matrix, img_height, img_width, transform_matrix, result)
+
+
+def dct_all_blocks(image_matrix, img_height, img_width, transform_matrix, result, handle=None):
+    """main_cublass.cu:197 / main_cublass_2.cu:197; the cuBLAS handle is ignored."""
+    _compat_call(compat_lib().b200dct_compat_dct, image_matrix, img_height, img_width, transform_matrix, result)
+
+
+def idct_all_blocks(image_matrix, img_height, img_width, transform_matrix, result, handle=None, dequant_in_place=False):
+    """main_cublass.cu:265 (const input) / main_cublass_2.cu:257 (input dequantised in place
+    when dequant_in_place=True, the v2 behaviour)."""
+    fn = compat_lib().b200dct_compat_idct_inplace_dequant if dequant_in_place else compat_lib().b200dct_compat_idct
+    _compat_call(fn, image_matrix, img_height, img_width, transform_matrix, result)

@@ -1,0 +1,525 @@
+// b200dct.cu -- host side of the C ABI declared in include/b200dct.h: plans, argument
+// checking, kernel-family selection, TMA descriptors, the pipelined host-buffer round
+// trip and the device-side MSE/PEEN accumulation.  Plain CUDA C++; no torch, no cuBLAS.
+#include "b200dct.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+#include "dct_kernels.cuh"
+
+namespace b200dct {
+// one launcher per translation unit of kernel instantiations (inst_*.cu)
+cudaError_t launch_direct_sparse(int mode, int qmode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_direct_dense(int mode, int qmode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_tma_sparse(int mode, int qmode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s);
+cudaError_t launch_tma_dense(int mode, int qmode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s);
+} // namespace b200dct
+
+using namespace b200dct;
+
+struct b200dct_plan {
+    float T[64];
+    float Q[64];
+    uint64_t mask;
+    bool sparse;     // T is bit-identical to Haweel's matrix
+    bool q_default;  // Q is the JPEG luminance table
+    bool q_fastdiv;  // every divisor is in the exhaustively proven set (integers 1..255)
+    int path;        // b200dct_path
+    CommonParams cp; // device-ready tables
+};
+
+static thread_local int tl_launches = 0;
+static thread_local const char *tl_path = "none";
+
+static void plan_refresh(b200dct_plan *pl)
+{
+    pl->sparse = true;
+    pl->q_default = true;
+    pl->q_fastdiv = true;
+    for (int k = 0; k < 64; k++) {
+        const float h = haweel(k / 8, k % 8);
+        if (memcmp(&h, &pl->T[k], 4) != 0 && !(h == 0.0f && pl->T[k] == 0.0f)) pl->sparse = false;
+        if (pl->Q[k] != jpeg_q(k)) pl->q_default = false;
+        const float d = pl->Q[k];
+        if (!(d >= 1.0f && d <= 255.0f && d == floorf(d))) pl->q_fastdiv = false;
+        pl->cp.q.d[k] = d;
+        pl->cp.q.neg_d[k] = -d;
+        pl->cp.q.rcp[k] = 1.0f / d; // IEEE RN on the host
+        pl->cp.q.keep[k] = ((pl->mask >> k) & 1) ? 0xffffffffu : 0u;
+        pl->cp.t.t[k] = pl->T[k];
+        pl->cp.t.tt[(k % 8) * 8 + k / 8] = pl->T[k];
+    }
+}
+
+static int qmode_of(const b200dct_plan *pl)
+{
+    if (!pl->q_fastdiv) return Q_PARAM_DIV;
+    if (pl->sparse && pl->q_default && pl->mask == ~(uint64_t)0) return Q_IMM;
+    return Q_PARAM;
+}
+
+extern "C" int b200dct_plan_create(b200dct_plan **out)
+{
+    if (!out) return B200DCT_ERR_ARG;
+    b200dct_plan *pl = new (std::nothrow) b200dct_plan;
+    if (!pl) return B200DCT_ERR_NOMEM;
+    for (int k = 0; k < 64; k++) {
+        pl->T[k] = haweel(k / 8, k % 8);
+        pl->Q[k] = jpeg_q(k);
+    }
+    pl->mask = ~(uint64_t)0;
+    pl->path = B200DCT_PATH_AUTO;
+    plan_refresh(pl);
+    *out = pl;
+    return B200DCT_OK;
+}
+
+extern "C" void b200dct_plan_destroy(b200dct_plan *pl) { delete pl; }
+
+extern "C" int b200dct_plan_set_quant(b200dct_plan *pl, const float *q)
+{
+    if (!pl || !q) return B200DCT_ERR_ARG;
+    for (int k = 0; k < 64; k++)
+        if (!isfinite(q[k]) || q[k] == 0.0f) return B200DCT_ERR_QUANT;
+    memcpy(pl->Q, q, sizeof(pl->Q));
+    plan_refresh(pl);
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_get_quant(const b200dct_plan *pl, float *q)
+{
+    if (!pl || !q) return B200DCT_ERR_ARG;
+    memcpy(q, pl->Q, sizeof(pl->Q));
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_set_transform(b200dct_plan *pl, const float *t)
+{
+    if (!pl || !t) return B200DCT_ERR_ARG;
+    memcpy(pl->T, t, sizeof(pl->T));
+    plan_refresh(pl);
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_set_transform_device(b200dct_plan *pl, const void *d_t)
+{
+    if (!pl || !d_t) return B200DCT_ERR_ARG;
+    float t[64];
+    cudaError_t e = cudaMemcpy(t, d_t, sizeof(t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    return b200dct_plan_set_transform(pl, t);
+}
+
+extern "C" int b200dct_plan_set_keep_mask(b200dct_plan *pl, uint64_t mask)
+{
+    if (!pl) return B200DCT_ERR_ARG;
+    pl->mask = mask;
+    plan_refresh(pl);
+    return B200DCT_OK;
+}
+
+extern "C" uint64_t b200dct_zigzag_mask(int k)
+{
+    static const unsigned char zz[64] = {
+        0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5,
+        12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+        58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    if (k >= 64) return ~(uint64_t)0;
+    uint64_t m = 0;
+    for (int i = 0; i < k; i++) m |= (uint64_t)1 << zz[i];
+    return m;
+}
+
+extern "C" int b200dct_plan_set_path(b200dct_plan *pl, b200dct_path path)
+{
+    if (!pl || path < B200DCT_PATH_AUTO || path > B200DCT_PATH_TMA) return B200DCT_ERR_ARG;
+    pl->path = path;
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_is_sparse(const b200dct_plan *pl) { return pl ? (pl->sparse ? 1 : 0) : B200DCT_ERR_ARG; }
+
+// ------------------------------------------------------------------ device info
+struct DevInfo {
+    int sms;
+    int smem_optin;
+    bool ok;
+};
+static DevInfo dev_info()
+{
+    static thread_local int cached_dev = -1;
+    static thread_local DevInfo info = {0, 0, false};
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return DevInfo{0, 0, false};
+    if (dev != cached_dev) {
+        info.ok = cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&info.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess;
+        cached_dev = dev;
+    }
+    return info;
+}
+
+// ------------------------------------------------------------------ TMA descriptors
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode()
+{
+    static encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+    });
+    return fn;
+}
+
+static size_t elem_size(int dt) { return dt == DT_F32 ? 4 : (dt == DT_I16 ? 2 : 1); }
+
+// Can this plane be addressed by the tile view of its dtype?
+static bool tma_plane_ok(const void *ptr, int dt, size_t pitch, int W)
+{
+    if (((uintptr_t)ptr & 15) || (pitch & 15)) return false;
+    if (dt == DT_F32) return (W % 32) == 0;
+    return (((size_t)W * elem_size(dt)) % 16) == 0;
+}
+
+static bool make_map(CUtensorMap *map, const void *ptr, int dt, size_t pitch, int H, int W)
+{
+    encode_tiled_fn enc = get_encode();
+    if (!enc) return false;
+    CUresult r;
+    if (dt == DT_F32) {
+        // {32 floats, W/32 segments, H rows}; box = 8 rows x 8 segments x 128 B, 128B swizzle
+        cuuint64_t dims[3] = {32, (cuuint64_t)(W / 32), (cuuint64_t)H};
+        cuuint64_t strides[2] = {128, (cuuint64_t)pitch};
+        cuuint32_t box[3] = {32, 8, 8};
+        cuuint32_t es[3] = {1, 1, 1};
+        r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
+        cuuint64_t strides[1] = {(cuuint64_t)pitch};
+        cuuint32_t box[2] = {256, 8};
+        cuuint32_t es[2] = {1, 1};
+        r = enc(map, dt == DT_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
+                const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS;
+}
+
+// ------------------------------------------------------------------ dispatch
+struct Plane {
+    const void *ptr;
+    int dt;
+    size_t pitch;
+};
+
+static int check_plane(const Plane &pl, int W, bool pixels)
+{
+    if (!pl.ptr) return B200DCT_ERR_ARG;
+    if (pixels ? (pl.dt != DT_F32 && pl.dt != DT_U8) : (pl.dt != DT_F32 && pl.dt != DT_I16)) return B200DCT_ERR_ARG;
+    if (pl.pitch < (size_t)W * elem_size(pl.dt)) return B200DCT_ERR_SHAPE;
+    const size_t a = pl.dt == DT_U8 ? 8 : 16;
+    if (((uintptr_t)pl.ptr % a) || (pl.pitch % a)) return B200DCT_ERR_ALIGN;
+    return B200DCT_OK;
+}
+
+static int tma_warps = 14; // warps per CTA of the persistent kernel (B200DCT_TMA_WARPS overrides)
+
+static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,
+               cudaStream_t stream)
+{
+    tl_launches = 0;
+    if (!pl) return B200DCT_ERR_ARG;
+    if (H <= 0 || W <= 0 || (H % 8) || (W % 8)) return B200DCT_ERR_SHAPE;
+    int rc;
+    if ((rc = check_plane(in, W, mode != MODE_INV)) != 0) return rc;
+    if ((rc = check_plane(out, W, mode != MODE_FWD)) != 0) return rc;
+    if (coef.ptr && (rc = check_plane(coef, W, false)) != 0) return rc;
+    if (mode == MODE_RT && in.dt != out.dt) return B200DCT_ERR_ARG;
+    if (shifted && (in.dt != DT_F32 || mode != MODE_FWD)) return B200DCT_ERR_ARG;
+
+    const DevInfo di = dev_info();
+    if (!di.ok) return B200DCT_ERR_NODEVICE;
+
+    const int pix = (mode == MODE_INV) ? out.dt : in.dt;
+    const int coef_dt = (mode == MODE_FWD) ? out.dt : (mode == MODE_INV ? in.dt : (coef.ptr ? coef.dt : DT_F32));
+    const int qmode = qmode_of(pl);
+    const int qm = (!pl->sparse && qmode == Q_IMM) ? Q_PARAM : qmode;
+
+    bool use_tma = pl->path != B200DCT_PATH_DIRECT && !shifted && get_encode() != nullptr &&
+                   tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
+                   (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
+    if (pl->path == B200DCT_PATH_TMA && !use_tma) return B200DCT_ERR_ALIGN;
+
+    if (use_tma) {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            const char *e = getenv("B200DCT_TMA_WARPS");
+            if (e && atoi(e) >= 1 && atoi(e) <= 14) tma_warps = atoi(e);
+        });
+        TmaParams P;
+        memset(&P, 0, sizeof(P));
+        if (!make_map(&P.in_map, in.ptr, in.dt, in.pitch, H, W) || !make_map(&P.out_map, out.ptr, out.dt, out.pitch, H, W))
+            return B200DCT_ERR_ARG;
+        if (coef.ptr && !make_map(&P.coef_map, coef.ptr, coef.dt, coef.pitch, H, W)) return B200DCT_ERR_ARG;
+        P.tiles_x = (uint32_t)((W + 255) / 256);
+        const unsigned long long nt = (unsigned long long)P.tiles_x * (unsigned long long)(H / 8);
+        if (nt > 0x7fffffffull) return B200DCT_ERR_SHAPE;
+        P.ntiles = (uint32_t)nt;
+        P.coef_dt = coef_dt;
+        P.has_coef = coef.ptr ? 1 : 0;
+        P.cp = pl->cp;
+        const int nw = tma_warps;
+        const size_t smem = (size_t)nw * WARP_SMEM_BYTES + (size_t)nw * 8 + 1024;
+        unsigned long long want = (nt + nw - 1) / nw;
+        const int grid = (int)(want < (unsigned long long)di.sms ? want : (unsigned long long)di.sms);
+        cudaError_t e = pl->sparse ? launch_tma_sparse(mode, qm, pix, P, grid, nw * 32, smem, stream)
+                                   : launch_tma_dense(mode, qm, pix, P, grid, nw * 32, smem, stream);
+        if (e != cudaSuccess) return (int)e;
+        tl_launches = 1;
+        tl_path = "tma";
+        return B200DCT_OK;
+    }
+
+    DirectParams P;
+    memset(&P, 0, sizeof(P));
+    P.in = in.ptr; P.in_pitch = in.pitch;
+    P.out = const_cast<void *>(out.ptr); P.out_pitch = out.pitch;
+    P.coef = const_cast<void *>(coef.ptr); P.coef_pitch = coef.pitch;
+    P.shifted = shifted; P.shifted_pitch = in.pitch;
+    P.bx = W / 8; P.by = H / 8;
+    P.coef_dt = coef_dt;
+    P.cp = pl->cp;
+    dim3 block(32, 4);
+    dim3 grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32));
+    if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
+    cudaError_t e = pl->sparse ? launch_direct_sparse(mode, qm, pix, P, grid, block, stream)
+                               : launch_direct_dense(mode, qm, pix, P, grid, block, stream);
+    if (e != cudaSuccess) return (int)e;
+    tl_launches = 1;
+    tl_path = "direct";
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_forward(const b200dct_plan *plan, const void *img, b200dct_dtype img_dt, size_t img_pitch,
+                               void *coef, b200dct_dtype coef_dt, size_t coef_pitch, void *shifted_or_null, int H,
+                               int W, void *stream)
+{
+    return run(plan, MODE_FWD, Plane{img, (int)img_dt, img_pitch}, Plane{coef, (int)coef_dt, coef_pitch},
+               Plane{nullptr, DT_F32, 0}, (float *)shifted_or_null, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int b200dct_inverse(const b200dct_plan *plan, const void *coef, b200dct_dtype coef_dt, size_t coef_pitch,
+                               void *img, b200dct_dtype img_dt, size_t img_pitch, int H, int W, void *stream)
+{
+    return run(plan, MODE_INV, Plane{coef, (int)coef_dt, coef_pitch}, Plane{img, (int)img_dt, img_pitch},
+               Plane{nullptr, DT_F32, 0}, nullptr, H, W, (cudaStream_t)stream);
+}
+
+extern "C" int b200dct_roundtrip(const b200dct_plan *plan, const void *img, b200dct_dtype in_dt, size_t in_pitch,
+                                 void *out, b200dct_dtype out_dt, size_t out_pitch, void *coef_or_null,
+                                 b200dct_dtype coef_dt, size_t coef_pitch, int H, int W, void *stream)
+{
+    return run(plan, MODE_RT, Plane{img, (int)in_dt, in_pitch}, Plane{out, (int)out_dt, out_pitch},
+               Plane{coef_or_null, (int)coef_dt, coef_pitch}, nullptr, H, W, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host-buffer round trip
+// Per-thread, per-device grow-only workspace: NCHUNK stream slots, each with an input
+// and an output chunk buffer.  Chunks are block-row stripes, so every chunk is itself a
+// valid image for the kernels (blocks are independent).
+namespace {
+constexpr int NSLOT = 4;
+struct HostPipe {
+    int dev = -1;
+    cudaStream_t st[NSLOT] = {};
+    void *din[NSLOT] = {};
+    void *dout[NSLOT] = {};
+    size_t cap_in = 0, cap_out = 0;
+    void release()
+    {
+        for (int i = 0; i < NSLOT; i++) {
+            if (din[i]) cudaFree(din[i]);
+            if (dout[i]) cudaFree(dout[i]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+            din[i] = dout[i] = nullptr;
+            st[i] = nullptr;
+        }
+        cap_in = cap_out = 0;
+        dev = -1;
+    }
+    ~HostPipe() {} // device memory is reclaimed with the context
+};
+thread_local HostPipe tl_pipe;
+} // namespace
+
+extern "C" int b200dct_roundtrip_host(const b200dct_plan *plan, const void *h_in, b200dct_dtype in_dt, void *h_out,
+                                      b200dct_dtype out_dt, int H, int W)
+{
+    if (!plan || !h_in || !h_out) return B200DCT_ERR_ARG;
+    if (H <= 0 || W <= 0 || (H % 8) || (W % 8)) return B200DCT_ERR_SHAPE;
+    if (in_dt != out_dt || (in_dt != B200DCT_F32 && in_dt != B200DCT_U8)) return B200DCT_ERR_ARG;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return B200DCT_ERR_NODEVICE;
+    const size_t es = elem_size((int)in_dt);
+    const size_t row = (size_t)W * es;
+    // ~16 MiB chunks, at least 8 rows, whole block-rows
+    long long rows = (long long)((16u << 20) / row) & ~7ll;
+    if (rows < 8) rows = 8;
+    if (rows > H) rows = H;
+    const size_t chunk_bytes = (size_t)rows * row;
+
+    HostPipe &hp = tl_pipe;
+    if (hp.dev != dev || hp.cap_in < chunk_bytes || hp.cap_out < chunk_bytes) {
+        hp.release();
+        for (int i = 0; i < NSLOT; i++) {
+            if (cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaMalloc(&hp.din[i], chunk_bytes) != cudaSuccess || cudaMalloc(&hp.dout[i], chunk_bytes) != cudaSuccess) {
+                hp.release();
+                return B200DCT_ERR_NOMEM;
+            }
+        }
+        hp.cap_in = hp.cap_out = chunk_bytes;
+        hp.dev = dev;
+    }
+    int launches = 0, rc = B200DCT_OK, slot = 0;
+    for (long long r0 = 0; r0 < H; r0 += rows, slot = (slot + 1) % NSLOT) {
+        const int h = (int)((H - r0) < rows ? (H - r0) : rows);
+        const size_t bytes = (size_t)h * row;
+        cudaStream_t s = hp.st[slot];
+        cudaError_t e = cudaMemcpyAsync(hp.din[slot], (const char *)h_in + (size_t)r0 * row, bytes, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+        rc = b200dct_roundtrip(plan, hp.din[slot], in_dt, row, hp.dout[slot], out_dt, row, nullptr, B200DCT_F32, 0, h, W, s);
+        if (rc != B200DCT_OK) break;
+        launches += tl_launches;
+        e = cudaMemcpyAsync((char *)h_out + (size_t)r0 * row, hp.dout[slot], bytes, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) { rc = (int)e; break; }
+    }
+    for (int i = 0; i < NSLOT; i++) {
+        cudaError_t e = cudaStreamSynchronize(hp.st[i]);
+        if (e != cudaSuccess && rc == B200DCT_OK) rc = (int)e;
+    }
+    tl_launches = launches;
+    return rc;
+}
+
+// ------------------------------------------------------------------ metrics
+template <class T>
+__global__ void k_metrics(const T *__restrict__ a, const T *__restrict__ b, size_t pitch_elems, int H, int W, double *acc)
+{
+    double se = 0.0, en = 0.0;
+    for (long long y = blockIdx.x; y < H; y += gridDim.x) {
+        const T *ra = a + (size_t)y * pitch_elems, *rb = b + (size_t)y * pitch_elems;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            const double va = (double)ra[x], d = va - (double)rb[x];
+            se += d * d;
+            en += va * va;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        se += __shfl_xor_sync(0xffffffffu, se, o);
+        en += __shfl_xor_sync(0xffffffffu, en, o);
+    }
+    __shared__ double s_se[32], s_en[32];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_se[w] = se; s_en[w] = en; }
+    __syncthreads();
+    if (w == 0) {
+        se = l < (blockDim.x >> 5) ? s_se[l] : 0.0;
+        en = l < (blockDim.x >> 5) ? s_en[l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            en += __shfl_xor_sync(0xffffffffu, en, o);
+        }
+        if (l == 0) { atomicAdd(&acc[0], se); atomicAdd(&acc[1], en); }
+    }
+}
+
+extern "C" int b200dct_metrics_accumulate(const void *ref_img, const void *test_img, b200dct_dtype dt, size_t pitch,
+                                          int H, int W, double *d_acc, void *stream)
+{
+    tl_launches = 0;
+    if (!ref_img || !test_img || !d_acc || H <= 0 || W <= 0) return B200DCT_ERR_ARG;
+    const DevInfo di = dev_info();
+    if (!di.ok) return B200DCT_ERR_NODEVICE;
+    int grid = di.sms * 8 < H ? di.sms * 8 : H;
+    if (dt == B200DCT_F32)
+        k_metrics<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)ref_img, (const float *)test_img, pitch / 4, H, W, d_acc);
+    else if (dt == B200DCT_U8)
+        k_metrics<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char *)ref_img, (const unsigned char *)test_img, pitch, H, W, d_acc);
+    else
+        return B200DCT_ERR_ARG;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    tl_launches = 1;
+    return B200DCT_OK;
+}
+
+// ------------------------------------------------------------------ self-test: constant division
+// Sweeps every float bit pattern x in [first, first+count) and compares the kernels'
+// three-FMA division by d against __fdiv_rn (the reference's div.rn.f32).  out[0] counts
+// finite x whose QUOTIENT bits differ, out[1] those whose quantised value
+// roundf(quotient) differs (the only thing the transform consumes).
+__global__ void k_selftest_div(float d, unsigned long long first, unsigned long long count, unsigned long long *out)
+{
+    const float nd = -d, r = 1.0f / d;
+    unsigned long long bad_q = 0, bad_c = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)(first + i));
+        if (!isfinite(x)) continue;
+        const float q0 = x * r;
+        const float e = __fmaf_rn(q0, nd, x);
+        const float q = __fmaf_rn(e, r, q0);
+        const float ref = __fdiv_rn(x, d);
+        if (__float_as_uint(q) != __float_as_uint(ref)) bad_q++;
+        if (__float_as_uint(roundf(q)) != __float_as_uint(roundf(ref))) bad_c++;
+    }
+    if (bad_q) atomicAdd(&out[0], bad_q);
+    if (bad_c) atomicAdd(&out[1], bad_c);
+}
+
+extern "C" int b200dct_selftest_division(float d, unsigned long long first, unsigned long long count,
+                                         unsigned long long *d_out2, void *stream)
+{
+    if (!d_out2 || !(d != 0.0f)) return B200DCT_ERR_ARG;
+    const DevInfo di = dev_info();
+    if (!di.ok) return B200DCT_ERR_NODEVICE;
+    k_selftest_div<<<di.sms * 16, 256, 0, (cudaStream_t)stream>>>(d, first, count, d_out2);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? B200DCT_OK : (int)e;
+}
+
+extern "C" int b200dct_last_launch_count(void) { return tl_launches; }
+extern "C" const char *b200dct_last_path(void) { return tl_path; }
+
+extern "C" const char *b200dct_error_string(int err)
+{
+    switch (err) {
+    case B200DCT_OK: return "ok";
+    case B200DCT_ERR_ARG: return "bad argument (NULL pointer, dtype not valid for that plane, or mixed pixel dtypes)";
+    case B200DCT_ERR_SHAPE: return "H and W must be positive multiples of 8 and pitch >= row bytes";
+    case B200DCT_ERR_ALIGN: return "pointer/pitch not aligned (16 B for f32/i16 planes, 8 B for u8), or TMA path forced on an unsuitable layout";
+    case B200DCT_ERR_NODEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case B200DCT_ERR_QUANT: return "quantisation entries must be finite and non-zero";
+    case B200DCT_ERR_NOMEM: return "out of memory";
+    default: return err > 0 ? cudaGetErrorString((cudaError_t)err) : "unknown error";
+    }
+}
+
+extern "C" int b200dct_version(void) { return B200DCT_VERSION; }

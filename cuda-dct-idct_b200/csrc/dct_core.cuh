@@ -1,0 +1,336 @@
+// dct_core.cuh -- register-resident 8x8 block transform core for sm_100a.
+//
+// One thread owns one 8x8 block as 32 packed float pairs (p[row][pair], pair j holds
+// columns 2j and 2j+1).  Both separable passes, the quantiser and the dequantiser run
+// on registers only: no shared memory, no shuffles, no barriers between the passes.
+//
+// Arithmetic contract (what makes the quantised coefficients bit-exact against the
+// reference kernels, see DESIGN.md "Arithmetic"):
+//   * every inner product is the reference's ordered chain of fused multiply-adds,
+//     summation index ascending, accumulator starting at +0.0f
+//     (cuda_matrix_dct main_newAppr.cu:193-197,206-209; cuda_matrix_idct :236-239,246-248;
+//      the same chains in cuda_matrix_dct_paper main_fastAppr.cu:203-227).  Terms whose
+//     T entry is exactly 0 are skipped: fma(0,x,s)==s bit-for-bit for finite x because
+//     the running sum is never -0.0f.
+//   * two independent chains are issued per instruction with Blackwell's packed
+//     fma.rn.f32x2 (SASS FFMA2); each half is an IEEE fma.rn, so packing changes
+//     nothing numerically.  In the column pass the two halves are adjacent columns and
+//     the T entry is a broadcast immediate; in the row pass the two halves are two
+//     output columns with the same sparsity pattern and the input is a broadcast
+//     register.
+//   * quantisation is a correctly rounded division (divide_matrices,
+//     utils_kernels.cu:42, PTX div.rn.f32) followed by round-half-away-from-zero.
+//     With a known divisor d and r = RN(1/d) the quotient is obtained with three FMAs
+//     (q0 = x*r; e = fma(-d,q0,x); q = fma(e,r,q0)), which is the correctly rounded
+//     x/d (Markstein); tests/test_gpu_div.py sweeps all 2^32 inputs per divisor.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <type_traits>
+#include <utility>
+
+namespace b200dct {
+
+// ---------------------------------------------------------------- static loops
+template <class F, int... I>
+__device__ __forceinline__ void sfor_impl(F &f, std::integer_sequence<int, I...>)
+{
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void sfor(F &&f)
+{
+    sfor_impl(f, std::make_integer_sequence<int, N>{});
+}
+#define IC(v) (decltype(v)::value)
+
+// ---------------------------------------------------------------- packed fp32
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
+
+// ---------------------------------------------------------------- constants
+// Haweel's matrix, spelled exactly as the reference does (double literals narrowed to
+// float, main_newAppr.cu:73-81) so that the bit patterns are the reference's.
+__host__ __device__ constexpr float haweel(int r, int c)
+{
+    constexpr float a = (float)0.35355339, h = (float)0.5, p = (float)0.4472136,
+                    q = (float)0.2236068, s = (float)0.70710678;
+    constexpr float t[64] = {
+        a, a, a, a, a, a, a, a,
+        h, h, 0, 0, 0, 0, -h, -h,
+        p, q, -q, -p, -p, -q, q, p,
+        0, 0, -s, 0, 0, s, 0, 0,
+        a, -a, -a, a, a, -a, -a, a,
+        h, -h, 0, 0, 0, 0, h, -h,
+        q, -p, p, -q, -q, p, -p, q,
+        0, 0, 0, -s, s, 0, 0, 0};
+    return t[r * 8 + c];
+}
+
+// JPEG luminance table (main_newAppr.cu:60-68).
+__host__ __device__ constexpr float jpeg_q(int k)
+{
+    constexpr float q[64] = {
+        16, 11, 10, 16, 24, 40, 51, 61,
+        12, 12, 14, 19, 26, 58, 60, 55,
+        14, 13, 16, 24, 40, 57, 69, 56,
+        14, 17, 22, 29, 51, 87, 80, 62,
+        18, 22, 37, 56, 68, 109, 103, 77,
+        24, 35, 55, 64, 81, 104, 113, 92,
+        49, 64, 78, 87, 103, 121, 120, 101,
+        72, 92, 95, 98, 112, 100, 103, 99};
+    return q[k];
+}
+
+// Runtime tables handed to the kernels by value (they live in the kernel-parameter
+// constant bank, so every use is a c[0x0][..] operand, not a load).
+struct QuantTables {
+    float neg_d[64];   // -Q
+    float rcp[64];     // RN(1/Q)
+    float d[64];       //  Q (dequantiser, and divisor of the exact-division fallback)
+    uint32_t keep[64]; // 0xffffffff kept / 0 dropped
+};
+struct DenseT {
+    float t[64];  // T[r][c]
+    float tt[64]; // T^T, so that {T[x][i],T[x+1][i]} is one aligned 8-byte constant
+};
+
+// ---------------------------------------------------------------- transform policies
+// A policy answers "coefficient multiplying input i in the chain of output a".
+//   forward  column pass: M[y][x] = sum_i T[y][i] X[i][x]   -> at(y,i) = T[y][i]
+//   forward  row    pass: Y[y][x] = sum_i M[y][i] T[x][i]   -> at(x,i) = T[x][i]
+//   inverse  column pass: M[y][x] = sum_i T[i][y] D[i][x]   -> at(y,i) = T[i][y]
+//   inverse  row    pass: R[y][x] = sum_i M[y][i] T[i][x]   -> at(x,i) = T[i][x]
+// so the inverse is the forward machinery with T transposed.
+template <bool INV>
+struct HaweelT {
+    static constexpr bool is_static = true;
+    __host__ __device__ static constexpr float at(int a, int i) { return INV ? haweel(i, a) : haweel(a, i); }
+    // row-pass output pairing: columns with identical sparsity patterns share an FFMA2
+    static constexpr int n_units = INV ? 4 : 5;
+    __host__ __device__ static constexpr int ua(int k)
+    {
+        constexpr int f[5] = {0, 2, 1, 3, 7}, v[4] = {0, 1, 2, 3};
+        return INV ? v[k] : f[k];
+    }
+    __host__ __device__ static constexpr int ub(int k)
+    {
+        constexpr int f[5] = {4, 6, 5, -1, -1}, v[4] = {7, 6, 5, 4};
+        return INV ? v[k] : f[k];
+    }
+};
+
+template <bool INV>
+struct RuntimeT {
+    static constexpr bool is_static = false;
+    const DenseT &m;
+    __device__ __forceinline__ explicit RuntimeT(const DenseT &mm) : m(mm) {}
+    __device__ __forceinline__ float at(int a, int i) const { return INV ? m.tt[a * 8 + i] : m.t[a * 8 + i]; }
+    // pair {at(x,i), at(x+1,i)} as one aligned 64-bit constant
+    __device__ __forceinline__ float2 at2(int x, int i) const
+    {
+        const float *base = INV ? m.t : m.tt; // INV: T[i][x],T[i][x+1]; FWD: Tt[i][x],Tt[i][x+1]
+        return *reinterpret_cast<const float2 *>(base + i * 8 + x);
+    }
+    static constexpr int n_units = 4;
+    __host__ __device__ static constexpr int ua(int k) { return 2 * k; }
+    __host__ __device__ static constexpr int ub(int k) { return 2 * k + 1; }
+};
+
+// ---------------------------------------------------------------- the two passes
+// Column pass, in place: for each column pair j, p[y][j] <- chain_i at(y,i) * p[i][j].
+template <class TP>
+__device__ __forceinline__ void col_pass(float2 (&p)[8][4], const TP &tp)
+{
+    sfor<4>([&](auto j) {
+        float2 in[8];
+        sfor<8>([&](auto i) { in[IC(i)] = p[IC(i)][IC(j)]; });
+        sfor<8>([&](auto y) {
+            float2 acc = make_float2(0.0f, 0.0f);
+            sfor<8>([&](auto i) {
+                if constexpr (TP::is_static) {
+                    constexpr float t = TP::at(IC(y), IC(i));
+                    if constexpr (t != 0.0f) acc = ffma2(in[IC(i)], bc(t), acc);
+                } else {
+                    acc = ffma2(in[IC(i)], bc(tp.at(IC(y), IC(i))), acc);
+                }
+            });
+            p[IC(y)][IC(j)] = acc;
+        });
+    });
+}
+
+// Row pass for one row: o[x] <- chain_i m[i] * at(x,i).
+template <class TP>
+__device__ __forceinline__ void row_pass(const float (&m)[8], float (&o)[8], const TP &tp)
+{
+    sfor<TP::n_units>([&](auto k) {
+        constexpr int xa = TP::ua(IC(k)), xb = TP::ub(IC(k));
+        if constexpr (xb >= 0) {
+            float2 acc = make_float2(0.0f, 0.0f);
+            sfor<8>([&](auto i) {
+                if constexpr (TP::is_static) {
+                    constexpr float ta = TP::at(xa, IC(i)), tb = TP::at(xb, IC(i));
+                    if constexpr (ta != 0.0f || tb != 0.0f)
+                        acc = ffma2(bc(m[IC(i)]), make_float2(ta, tb), acc);
+                } else {
+                    acc = ffma2(bc(m[IC(i)]), tp.at2(xa, IC(i)), acc);
+                }
+            });
+            o[xa] = acc.x;
+            o[xb] = acc.y;
+        } else {
+            float acc = 0.0f;
+            sfor<8>([&](auto i) {
+                if constexpr (TP::is_static) {
+                    constexpr float t = TP::at(xa, IC(i));
+                    if constexpr (t != 0.0f) acc = __fmaf_rn(m[IC(i)], t, acc);
+                } else {
+                    acc = __fmaf_rn(m[IC(i)], tp.at(xa, IC(i)), acc);
+                }
+            });
+            o[xa] = acc;
+        }
+    });
+}
+
+// ---------------------------------------------------------------- quantiser policies
+// QImm: the JPEG table as immediates, all coefficients kept (the reference's only
+// configuration).  QParam: any table / mask, from the parameter constant bank.
+struct QImm {
+    static constexpr bool masked = false;
+    static constexpr bool fastdiv = true;
+    __device__ __forceinline__ float neg_d(int k) const { return -jpeg_q(k); }
+    __device__ __forceinline__ float rcp(int k) const { return 1.0f / jpeg_q(k); } // constant-folded, RN
+    __device__ __forceinline__ float d(int k) const { return jpeg_q(k); }
+    __device__ __forceinline__ uint32_t keep(int) const { return 0xffffffffu; }
+};
+template <bool MASKED, bool FASTDIV>
+struct QParam {
+    static constexpr bool masked = MASKED;
+    static constexpr bool fastdiv = FASTDIV;
+    const QuantTables &q;
+    __device__ __forceinline__ explicit QParam(const QuantTables &qq) : q(qq) {}
+    __device__ __forceinline__ float neg_d(int k) const { return q.neg_d[k]; }
+    __device__ __forceinline__ float rcp(int k) const { return q.rcp[k]; }
+    __device__ __forceinline__ float d(int k) const { return q.d[k]; }
+    __device__ __forceinline__ uint32_t keep(int k) const { return q.keep[k]; }
+};
+
+// round(y / Q[k]) exactly as divide_matrices (utils_kernels.cu:42): IEEE division, then
+// round half away from zero (nvcc lowers roundf to copysign(0.5) + add.rz + cvt.rzi).
+template <class QP>
+__device__ __forceinline__ float quantise(float y, int k, const QP &qp)
+{
+    float q;
+    if constexpr (QP::fastdiv) {
+        const float r = qp.rcp(k);
+        const float q0 = y * r;
+        const float e = __fmaf_rn(q0, qp.neg_d(k), y);
+        q = __fmaf_rn(e, r, q0);
+    } else {
+        q = __fdiv_rn(y, qp.d(k));
+    }
+    float c = roundf(q);
+    if constexpr (QP::masked) c = __uint_as_float(__float_as_uint(c) & qp.keep(k));
+    return c;
+}
+
+// ---------------------------------------------------------------- whole-block stages
+// p holds pixels-128 on entry and the quantised coefficients C on exit.
+template <class TF, class QP>
+__device__ __forceinline__ void forward_block(float2 (&p)[8][4], const TF &tf, const QP &qp)
+{
+    col_pass(p, tf);
+    sfor<8>([&](auto y) {
+        float m[8], o[8];
+        sfor<4>([&](auto j) {
+            m[2 * IC(j)] = p[IC(y)][IC(j)].x;
+            m[2 * IC(j) + 1] = p[IC(y)][IC(j)].y;
+        });
+        row_pass(m, o, tf);
+        sfor<4>([&](auto j) {
+            p[IC(y)][IC(j)].x = quantise(o[2 * IC(j)], IC(y) * 8 + 2 * IC(j), qp);
+            p[IC(y)][IC(j)].y = quantise(o[2 * IC(j) + 1], IC(y) * 8 + 2 * IC(j) + 1, qp);
+        });
+    });
+}
+
+// p holds quantised coefficients C on entry and R = T^T.(C*Q).T on exit (no +128).
+template <class TI, class QP>
+__device__ __forceinline__ void inverse_block(float2 (&p)[8][4], const TI &ti, const QP &qp)
+{
+    sfor<8>([&](auto y) {
+        sfor<4>([&](auto j) {
+            p[IC(y)][IC(j)].x *= qp.d(IC(y) * 8 + 2 * IC(j));     // multiply_matrices, utils_kernels.cu:55
+            p[IC(y)][IC(j)].y *= qp.d(IC(y) * 8 + 2 * IC(j) + 1);
+        });
+    });
+    col_pass(p, ti);
+    sfor<8>([&](auto y) {
+        float m[8], o[8];
+        sfor<4>([&](auto j) {
+            m[2 * IC(j)] = p[IC(y)][IC(j)].x;
+            m[2 * IC(j) + 1] = p[IC(y)][IC(j)].y;
+        });
+        row_pass(m, o, ti);
+        sfor<4>([&](auto j) { p[IC(y)][IC(j)] = make_float2(o[2 * IC(j)], o[2 * IC(j) + 1]); });
+    });
+}
+
+// ---------------------------------------------------------------- element conversions
+// u8 -> (float)b - 128 in two ops: PRMT builds 0x4B0000bb = 2^23 + b, one FADD removes
+// 2^23 + 128 (exact).  Equivalent to convertToFloat (utils.cu:13) then sub_matrix_scalar
+// (utils_kernels.cu:16).
+__device__ __forceinline__ float u8_shifted(uint32_t word, int byte)
+{
+    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7440u | (uint32_t)byte);
+    return __uint_as_float(bits) - 8388736.0f;
+}
+__device__ __forceinline__ float u8_to_float(uint32_t word, int byte)
+{
+    const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7440u | (uint32_t)byte);
+    return __uint_as_float(bits) - 8388608.0f;
+}
+// float pixel -> u8 as convertToUnsignedChar (utils.cu:21): clamp to [0,255], truncate.
+// Returns 2^23 + trunc(v) as float bits; the low byte is the pixel.
+__device__ __forceinline__ uint32_t pixel_u8_bits(float v)
+{
+    v = fminf(fmaxf(v, 0.0f), 255.0f);
+    return __float_as_uint(__fadd_rz(v, 8388608.0f));
+}
+__device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d)
+{
+    const uint32_t lo = __byte_perm(pixel_u8_bits(a), pixel_u8_bits(b), 0x0040);
+    const uint32_t hi = __byte_perm(pixel_u8_bits(c), pixel_u8_bits(d), 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+}
+// integer-valued float coefficient -> saturating int16
+__device__ __forceinline__ uint32_t pack2_i16(float a, float b)
+{
+    short ia, ib;
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(ia) : "f"(a));
+    asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(ib) : "f"(b));
+    return ((uint32_t)(unsigned short)ia) | ((uint32_t)(unsigned short)ib << 16);
+}
+__device__ __forceinline__ float i16_lo(uint32_t w) { return (float)(short)(w & 0xffffu); }
+__device__ __forceinline__ float i16_hi(uint32_t w) { return (float)((int)w >> 16); }
+
+} // namespace b200dct

@@ -1,0 +1,421 @@
+// dct_kernels.cuh -- the two kernel families built on dct_core.cuh.
+//
+//   k_direct : one thread per 8x8 block, 128-bit LDG/STG straight from/to HBM.  Works for
+//              any H,W multiple of 8 and any aligned pitch; also carries the
+//              "input overwritten with X-128" side effect of the reference's dct_*
+//              functions (main_newAppr.cu:273) for the compat wrappers.
+//   k_tma    : persistent kernel, one CTA per SM.  Every warp runs its own two-buffer
+//              pipeline: lane 0 issues a TMA tile load (8 image rows x 32 blocks) into a
+//              128B-swizzled shared-memory buffer and all lanes wait on the warp's
+//              mbarrier, pull their block into registers with conflict-free LDS.128,
+//              immediately re-arm the buffer with the next tile's TMA load, transform in
+//              registers, write the result tile to a second swizzled buffer and hand it
+//              to a TMA store.  No __syncthreads anywhere; HBM sees only full 1 KiB row
+//              segments in both directions.
+#pragma once
+
+#include <cuda.h>
+
+#include "dct_core.cuh"
+
+namespace b200dct {
+
+enum { MODE_FWD = 0, MODE_INV = 1, MODE_RT = 2 };
+enum { DT_F32 = 0, DT_U8 = 1, DT_I16 = 2, DT_NONE = -1 };
+// quantiser variants: 0 = JPEG immediates, all kept; 1 = parameter tables, fast exact
+// division, mask applied; 2 = parameter tables, __fdiv_rn (divisors outside the proven set)
+enum { Q_IMM = 0, Q_PARAM = 1, Q_PARAM_DIV = 2 };
+
+struct CommonParams {
+    QuantTables q;
+    DenseT t;
+};
+
+template <int QMODE>
+struct QSel;
+template <>
+struct QSel<Q_IMM> {
+    using type = QImm;
+    __device__ __forceinline__ static QImm make(const QuantTables &) { return QImm{}; }
+};
+template <>
+struct QSel<Q_PARAM> {
+    using type = QParam<true, true>;
+    __device__ __forceinline__ static type make(const QuantTables &q) { return type(q); }
+};
+template <>
+struct QSel<Q_PARAM_DIV> {
+    using type = QParam<true, false>;
+    __device__ __forceinline__ static type make(const QuantTables &q) { return type(q); }
+};
+
+// Runs the selected stages on a block held in p.
+//   FWD: pixels-128 -> C      INV: C -> R      RT: pixels-128 -> (C via emit_coef) -> R
+template <int MODE, bool SPARSE, int QMODE, class EmitCoef>
+__device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams &cp, EmitCoef &&emit_coef)
+{
+    auto qp = QSel<QMODE>::make(cp.q);
+    if constexpr (MODE != MODE_INV) {
+        if constexpr (SPARSE) forward_block(p, HaweelT<false>{}, qp);
+        else forward_block(p, RuntimeT<false>(cp.t), qp);
+    }
+    if constexpr (MODE == MODE_RT) emit_coef(p);
+    if constexpr (MODE != MODE_FWD) {
+        if constexpr (SPARSE) inverse_block(p, HaweelT<true>{}, qp);
+        else inverse_block(p, RuntimeT<true>(cp.t), qp);
+    }
+}
+
+// ============================================================== direct family
+struct DirectParams {
+    const void *in;   // FWD/RT: pixels (PIX dtype); INV: coefficients (coef_dt)
+    void *out;        // FWD: coefficients (coef_dt); INV/RT: pixels (PIX dtype)
+    void *coef;       // RT only: optional coefficient plane (coef_dt), else NULL
+    float *shifted;   // FWD only: optional img-128 write-back (f32), else NULL
+    size_t in_pitch, out_pitch, coef_pitch, shifted_pitch; // bytes
+    int bx, by;       // blocks per row / block rows
+    int coef_dt;      // DT_F32 / DT_I16
+    CommonParams cp;
+};
+
+// ---- per-row global accessors (one 8-pixel row of one block) ----
+__device__ __forceinline__ void ld_row_f32(const void *base, float2 (&r)[4])
+{
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(base));
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(base) + 1);
+    r[0] = make_float2(a.x, a.y); r[1] = make_float2(a.z, a.w);
+    r[2] = make_float2(b.x, b.y); r[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void st_row_f32(void *base, const float2 (&r)[4])
+{
+    reinterpret_cast<float4 *>(base)[0] = make_float4(r[0].x, r[0].y, r[1].x, r[1].y);
+    reinterpret_cast<float4 *>(base)[1] = make_float4(r[2].x, r[2].y, r[3].x, r[3].y);
+}
+__device__ __forceinline__ void unpack_u8_shifted(uint2 w, float2 (&r)[4])
+{
+    r[0] = make_float2(u8_shifted(w.x, 0), u8_shifted(w.x, 1));
+    r[1] = make_float2(u8_shifted(w.x, 2), u8_shifted(w.x, 3));
+    r[2] = make_float2(u8_shifted(w.y, 0), u8_shifted(w.y, 1));
+    r[3] = make_float2(u8_shifted(w.y, 2), u8_shifted(w.y, 3));
+}
+__device__ __forceinline__ uint2 pack_u8_plus128(const float2 (&r)[4])
+{
+    uint2 w;
+    w.x = pack4_u8(r[0].x + 128.0f, r[0].y + 128.0f, r[1].x + 128.0f, r[1].y + 128.0f);
+    w.y = pack4_u8(r[2].x + 128.0f, r[2].y + 128.0f, r[3].x + 128.0f, r[3].y + 128.0f);
+    return w;
+}
+__device__ __forceinline__ uint4 pack_i16(const float2 (&r)[4])
+{
+    return make_uint4(pack2_i16(r[0].x, r[0].y), pack2_i16(r[1].x, r[1].y),
+                      pack2_i16(r[2].x, r[2].y), pack2_i16(r[3].x, r[3].y));
+}
+__device__ __forceinline__ void unpack_i16(uint4 w, float2 (&r)[4])
+{
+    r[0] = make_float2(i16_lo(w.x), i16_hi(w.x)); r[1] = make_float2(i16_lo(w.y), i16_hi(w.y));
+    r[2] = make_float2(i16_lo(w.z), i16_hi(w.z)); r[3] = make_float2(i16_lo(w.w), i16_hi(w.w));
+}
+__device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
+{
+    sfor<4>([&](auto j) { r[IC(j)] = fadd2(r[IC(j)], bc(s)); });
+}
+
+template <int MODE, bool SPARSE, int QMODE, int PIX>
+__global__ void __launch_bounds__(128) k_direct(const __grid_constant__ DirectParams P)
+{
+    // CTA = 32 block-columns x 4 block-rows; grid.x walks block-rows (no 65535 limit),
+    // grid.y walks groups of 32 block-columns.  Lanes of a warp are horizontally adjacent
+    // blocks, so each row access of a warp covers one contiguous 1 KiB segment.
+    const int bxi = blockIdx.y * 32 + threadIdx.x;
+    const long long by = (long long)blockIdx.x * 4 + threadIdx.y;
+    if (bxi >= P.bx || by >= P.by) return;
+
+    float2 p[8][4];
+    // ---- load
+    if constexpr (MODE == MODE_INV) {
+        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch;
+        if (P.coef_dt == DT_F32) {
+            sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+        } else {
+            sfor<8>([&](auto r) {
+                unpack_i16(__ldg(reinterpret_cast<const uint4 *>(src + IC(r) * P.in_pitch + (size_t)bxi * 16)), p[IC(r)]);
+            });
+        }
+    } else if constexpr (PIX == DT_F32) {
+        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
+        sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch, p[IC(r)]); });
+        sfor<8>([&](auto r) { shift_row(p[IC(r)], -128.0f); }); // sub_matrix_scalar, utils_kernels.cu:16
+        if constexpr (MODE == MODE_FWD) {
+            if (P.shifted) {
+                char *dst = (char *)P.shifted + (size_t)by * 8 * P.shifted_pitch + (size_t)bxi * 32;
+                sfor<8>([&](auto r) { st_row_f32(dst + IC(r) * P.shifted_pitch, p[IC(r)]); });
+            }
+        }
+    } else {
+        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
+        sfor<8>([&](auto r) {
+            unpack_u8_shifted(__ldg(reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch)), p[IC(r)]);
+        });
+    }
+
+    auto store_coef = [&](void *plane, size_t pitch, float2 (&c)[8][4]) {
+        char *dst = (char *)plane + (size_t)by * 8 * pitch;
+        if (P.coef_dt == DT_F32) {
+            sfor<8>([&](auto r) { st_row_f32(dst + IC(r) * pitch + (size_t)bxi * 32, c[IC(r)]); });
+        } else {
+            sfor<8>([&](auto r) {
+                *reinterpret_cast<uint4 *>(dst + IC(r) * pitch + (size_t)bxi * 16) = pack_i16(c[IC(r)]);
+            });
+        }
+    };
+
+    run_block<MODE, SPARSE, QMODE>(p, P.cp, [&](float2 (&c)[8][4]) {
+        if (P.coef) store_coef(P.coef, P.coef_pitch, c);
+    });
+
+    // ---- store
+    if constexpr (MODE == MODE_FWD) {
+        store_coef(P.out, P.out_pitch, p);
+    } else if constexpr (PIX == DT_F32) {
+        char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 32;
+        sfor<8>([&](auto r) {
+            shift_row(p[IC(r)], 128.0f); // add_matrix_scalar, utils_kernels.cu:29
+            st_row_f32(dst + IC(r) * P.out_pitch, p[IC(r)]);
+        });
+    } else {
+        char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 8;
+        sfor<8>([&](auto r) { *reinterpret_cast<uint2 *>(dst + IC(r) * P.out_pitch) = pack_u8_plus128(p[IC(r)]); });
+    }
+}
+
+// ============================================================== TMA family
+// Tile = 8 image rows x 32 blocks (256 pixels).  Shared-memory images of a tile:
+//   f32 : 8 KiB, rows of 1 KiB = 8 segments of 128 B, hardware SWIZZLE_128B: the 16-byte
+//         chunk c of segment s sits at chunk c^s.  Lane l owns segment l>>2, chunks
+//         2(l&3), 2(l&3)+1, so a quarter-warp's LDS.128/STS.128 covers 8 distinct chunk
+//         positions: conflict-free (an unswizzled 32-byte lane stride is 2-way).
+//   u8  : 2 KiB, rows of 256 B, lane l owns bytes 8l..8l+7 (LDS.64, conflict-free).
+//   i16 : 4 KiB, rows of 512 B, lane l owns bytes 16l..16l+15 (LDS.128, conflict-free).
+struct TmaParams {
+    CUtensorMap in_map;   // FWD/RT: pixels; INV: coefficients
+    CUtensorMap out_map;  // FWD: coefficients; INV/RT: pixels
+    CUtensorMap coef_map; // RT with coefficient output
+    uint32_t tiles_x;     // tiles per tile-row
+    uint32_t ntiles;
+    int coef_dt;          // DT_F32 / DT_I16
+    int has_coef;         // RT: also emit the coefficient plane
+    CommonParams cp;
+};
+
+constexpr int TILE_BUF_BYTES = 8192;
+constexpr int WARP_SMEM_BYTES = 2 * TILE_BUF_BYTES;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// f32 tiles use the 3-d view {32 floats, W/32 segments, H rows}; u8/i16 tiles the 2-d view.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float4 lds128(uint32_t a)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint2 lds64u(uint32_t a)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts64u(uint32_t a, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Swizzled f32 tile accessors.  off0 = byte offset of the lane's first 16-byte chunk in a
+// tile row; the second chunk is off0 ^ 16.
+__device__ __forceinline__ uint32_t f32_tile_off0(int lane)
+{
+    return (uint32_t)((lane >> 2) * 128 + (((2 * (lane & 3)) ^ (lane >> 2)) & 7) * 16);
+}
+__device__ __forceinline__ void tile_ld_f32(uint32_t buf, uint32_t off0, float2 (&p)[8][4])
+{
+    sfor<8>([&](auto r) {
+        const float4 a = lds128(buf + IC(r) * 1024 + off0);
+        const float4 b = lds128(buf + IC(r) * 1024 + (off0 ^ 16u));
+        p[IC(r)][0] = make_float2(a.x, a.y); p[IC(r)][1] = make_float2(a.z, a.w);
+        p[IC(r)][2] = make_float2(b.x, b.y); p[IC(r)][3] = make_float2(b.z, b.w);
+    });
+}
+__device__ __forceinline__ void tile_st_f32(uint32_t buf, uint32_t off0, const float2 (&p)[8][4])
+{
+    sfor<8>([&](auto r) {
+        sts128(buf + IC(r) * 1024 + off0, make_float4(p[IC(r)][0].x, p[IC(r)][0].y, p[IC(r)][1].x, p[IC(r)][1].y));
+        sts128(buf + IC(r) * 1024 + (off0 ^ 16u), make_float4(p[IC(r)][2].x, p[IC(r)][2].y, p[IC(r)][3].x, p[IC(r)][3].y));
+    });
+}
+
+template <int DT>
+__device__ __forceinline__ uint32_t tile_bytes()
+{
+    return DT == DT_F32 ? 8192u : (DT == DT_I16 ? 4096u : 2048u);
+}
+
+template <int MODE, bool SPARSE, int QMODE, int PIX>
+__global__ void __launch_bounds__(448, 1) k_tma(const __grid_constant__ TmaParams P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 1 KiB alignment: the 128B swizzle pattern is a function of address bits 7..9
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const uint32_t in_buf = smem_base + warp * WARP_SMEM_BYTES;
+    const uint32_t out_buf = in_buf + TILE_BUF_BYTES;
+    const uint32_t bar = smem_base + nwarps * WARP_SMEM_BYTES + warp * 8;
+    const uint32_t off0 = f32_tile_off0(lane);
+
+    // tiles are dealt round-robin over all resident warps (CTA-minor), so the warps that
+    // are in flight at any moment cover one contiguous window of the image
+    const uint32_t stride = gridDim.x * nwarps;
+    uint32_t tile = warp * gridDim.x + blockIdx.x;
+
+    const bool in_is_f32 = (MODE == MODE_INV) ? (P.coef_dt == DT_F32) : (PIX == DT_F32);
+    const uint32_t in_bytes = (MODE == MODE_INV) ? (P.coef_dt == DT_F32 ? 8192u : 4096u) : tile_bytes<PIX>();
+
+    auto issue_load = [&](uint32_t t) {
+        const int ty = (int)(t / P.tiles_x), tx = (int)(t - (uint32_t)ty * P.tiles_x);
+        mbar_expect_tx(bar, in_bytes);
+        if (in_is_f32) tma_load_3d(in_buf, &P.in_map, bar, 0, tx * 8, ty * 8);
+        else tma_load_2d(in_buf, &P.in_map, bar, tx * 256, ty * 8);
+    };
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < P.ntiles) issue_load(tile);
+    }
+    __syncwarp();
+
+    uint32_t parity = 0;
+    for (; tile < P.ntiles; tile += stride) {
+        const int ty = (int)(tile / P.tiles_x), tx = (int)(tile - (uint32_t)ty * P.tiles_x);
+        mbar_wait(bar, parity);
+        parity ^= 1;
+
+        float2 p[8][4];
+        // ---- shared -> registers
+        if constexpr (MODE == MODE_INV) {
+            if (P.coef_dt == DT_F32) tile_ld_f32(in_buf, off0, p);
+            else sfor<8>([&](auto r) { unpack_i16(lds128u(in_buf + IC(r) * 512 + lane * 16), p[IC(r)]); });
+        } else if constexpr (PIX == DT_F32) {
+            tile_ld_f32(in_buf, off0, p);
+            sfor<8>([&](auto r) { shift_row(p[IC(r)], -128.0f); });
+        } else {
+            sfor<8>([&](auto r) { unpack_u8_shifted(lds64u(in_buf + IC(r) * 256 + lane * 8), p[IC(r)]); });
+        }
+        // every lane has consumed its part of in_buf: re-arm it with the next tile
+        __syncwarp();
+        const uint32_t next = tile + stride;
+        if (lane == 0 && next < P.ntiles) issue_load(next);
+
+        auto put_coef_tile = [&](const CUtensorMap *map, float2 (&c)[8][4]) {
+            if (lane == 0) tma_store_wait_read(); // previous store has drained out_buf
+            __syncwarp();
+            if (P.coef_dt == DT_F32) tile_st_f32(out_buf, off0, c);
+            else sfor<8>([&](auto r) { sts128u(out_buf + IC(r) * 512 + lane * 16, pack_i16(c[IC(r)])); });
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (P.coef_dt == DT_F32) tma_store_3d(map, out_buf, 0, tx * 8, ty * 8);
+                else tma_store_2d(map, out_buf, tx * 256, ty * 8);
+                tma_store_commit();
+            }
+        };
+
+        run_block<MODE, SPARSE, QMODE>(p, P.cp, [&](float2 (&c)[8][4]) {
+            if (P.has_coef) put_coef_tile(&P.coef_map, c);
+        });
+
+        // ---- registers -> shared -> HBM
+        if constexpr (MODE == MODE_FWD) {
+            put_coef_tile(&P.out_map, p);
+        } else {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+            if constexpr (PIX == DT_F32) {
+                sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); });
+                tile_st_f32(out_buf, off0, p);
+            } else {
+                sfor<8>([&](auto r) { sts64u(out_buf + IC(r) * 256 + lane * 8, pack_u8_plus128(p[IC(r)])); });
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (PIX == DT_F32) tma_store_3d(&P.out_map, out_buf, 0, tx * 8, ty * 8);
+                else tma_store_2d(&P.out_map, out_buf, tx * 256, ty * 8);
+                tma_store_commit();
+            }
+        }
+    }
+    if (lane == 0) tma_store_wait_read();
+}
+
+} // namespace b200dct

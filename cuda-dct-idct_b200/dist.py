@@ -1,0 +1,89 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), block-row stripes, no collective on
+the data path.  torch.distributed is used only for the barrier, the max-over-ranks timing
+reduction and the OPTIONAL final gather of the stripes (NCCL over NVLink on GPUs, gloo on
+CPU for the tests)."""
+from __future__ import annotations
+
+import os
+
+from .stripes import stripe_rows
+
+
+def env_rank():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def init(backend: str | None = None):
+    """Initialise torch.distributed from the torchrun environment (no-op for 1 rank).
+    Returns (rank, local_rank, world_size)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = env_rank()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    return rank, local_rank, world
+
+
+def barrier():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """MAX all-reduce of a scalar (the slowest rank defines the step time)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def my_stripe(H: int):
+    rank, _, world = env_rank()
+    return stripe_rows(H, world, rank)
+
+
+def gather_stripes(stripe, H: int, dst: int = 0):
+    """Optional final gather of the per-rank block-row stripes of an H-row image onto rank
+    `dst` (reported separately from kernel throughput).  Stripes may differ by one
+    block-row, so this is an all_gather of padded stripes followed by trimming."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return stripe
+    world, rank = dist.get_world_size(), dist.get_rank()
+    spans = [stripe_rows(H, world, r) for r in range(world)]
+    max_rows = max(b - a for a, b in spans)
+    pad = torch.zeros((max_rows, stripe.shape[1]), dtype=stripe.dtype, device=stripe.device)
+    pad[: stripe.shape[0]] = stripe
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    if rank != dst:
+        return None
+    return torch.cat([p[: b - a] for p, (a, b) in zip(parts, spans)], 0)

@@ -1,0 +1,168 @@
+/*
+ * b200dct.h -- C ABI of the B200-native 8x8 block-transform path.
+ *
+ * This is the drop-in boundary for the reference's host entry points.  The reference
+ * (GerryDps/CUDA-DCT-IDCT) has no FFI or header: each program forward-declares two free
+ * C++ functions and calls them from main() (main_newAppr.cu:23-24,99,120).  The entry
+ * points below are what a binding for that path binds; the C++ wrappers with the
+ * reference's exact (mangled) signatures live in b200dct_compat.h and are implemented on
+ * top of this ABI.
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  -------------------------------
+ *   dct_all_blocks_cuda   main_newAppr.cu:252-291          b200dct_forward
+ *                         main_fastAppr.cu:303-359
+ *   idct_all_blocks_cuda  main_newAppr.cu:293-332          b200dct_inverse
+ *                         main_fastAppr.cu:361-417
+ *   dct_all_blocks        main_cublass.cu:197-260          b200dct_forward   (dense T)
+ *                         main_cublass_2.cu:197-252
+ *   idct_all_blocks       main_cublass.cu:265-327          b200dct_inverse   (dense T)
+ *                         main_cublass_2.cu:257-311
+ *   dct_* followed by idct_* (main_newAppr.cu:99,120)      b200dct_roundtrip (one fused pass)
+ *   cudaMemcpyToSymbol(const_quant_matrix, ...)            b200dct_plan_set_quant
+ *                         main_newAppr.cu:19,70
+ *   transform_matrix device argument main_newAppr.cu:73-95 b200dct_plan_set_transform
+ *   convertToFloat / convertToUnsignedChar utils.cu:10-24  dtype B200DCT_U8 on either side
+ *   cudaMalloc/cudaMemcpy around the calls, main_newAppr.cu:88-95,103,124
+ *                                                          b200dct_roundtrip_host
+ *
+ * Conventions: images are single-channel, row-major; H and W are multiples of 8 (the
+ * reference silently computes garbage otherwise, main_newAppr.cu:261-262; here it is an
+ * error).  Pitches are in BYTES.  All image/coefficient pointers of the device entry
+ * points are caller-owned DEVICE pointers; nothing is allocated per call.  `stream` is a
+ * cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ * asynchronous on `stream` and re-entrant.  Every function returns 0 on success or a
+ * negative B200DCT_ERR_* / positive cudaError_t value; nothing ever calls exit().
+ * A batch of B images of H rows stored back to back is one image of B*H rows (blocks
+ * are independent), so there is no batch argument.
+ *
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200DCT_H
+#define B200DCT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DCT_VERSION 100
+
+typedef enum b200dct_dtype {
+    B200DCT_F32 = 0, /* float pixels / integer-valued float coefficients (the reference's type) */
+    B200DCT_U8 = 1,  /* 8-bit pixels: convertToFloat on load, clamp+truncate on store (utils.cu:10-24) */
+    B200DCT_I16 = 2  /* compact coefficients (saturating); coefficient planes only */
+} b200dct_dtype;
+
+enum {
+    B200DCT_OK = 0,
+    B200DCT_ERR_ARG = -1,     /* NULL pointer, bad dtype for that role, bad plan */
+    B200DCT_ERR_SHAPE = -2,   /* H or W not a positive multiple of 8, or pitch < row bytes */
+    B200DCT_ERR_ALIGN = -3,   /* pointer or pitch not aligned for vector access (16 B f32/i16, 8 B u8) */
+    B200DCT_ERR_NODEVICE = -4,/* no usable CUDA device */
+    B200DCT_ERR_QUANT = -5,   /* Q entry not finite or zero */
+    B200DCT_ERR_NOMEM = -6
+};
+
+/* Which kernel family a call may use.  AUTO picks TMA when the layout allows it
+ * (f32: W % 32 == 0; u8: W % 16 == 0 ...), otherwise DIRECT. */
+typedef enum b200dct_path {
+    B200DCT_PATH_AUTO = 0,
+    B200DCT_PATH_DIRECT = 1, /* one thread per block, vector LDG/STG */
+    B200DCT_PATH_TMA = 2     /* per-warp TMA tiles through swizzled shared memory */
+} b200dct_path;
+
+typedef struct b200dct_plan b200dct_plan;
+
+/* A plan owns the small state the reference keeps in globals: T (64 floats), Q (64
+ * floats), and the retained-coefficient mask.  Defaults: Haweel's T
+ * (main_newAppr.cu:73-81), the JPEG luminance Q (main_newAppr.cu:60-68), all 64
+ * coefficients kept.  Plans are immutable while a call using them is being issued;
+ * they hold no device memory. */
+int b200dct_plan_create(b200dct_plan **plan);
+void b200dct_plan_destroy(b200dct_plan *plan);
+
+/* q: 64 floats in HOST memory, row-major Q[row*8+col] (index = threadIdx.y*8+threadIdx.x
+ * in utils_kernels.cu:42,55).  Replaces cudaMemcpyToSymbol(const_quant_matrix,...). */
+int b200dct_plan_set_quant(b200dct_plan *plan, const float *q);
+int b200dct_plan_get_quant(const b200dct_plan *plan, float *q_out);
+
+/* t: 64 floats in HOST memory, row-major.  If it is bit-identical to Haweel's matrix the
+ * sparse compile-time kernels are used, otherwise the dense ("exact DCT") kernels. */
+int b200dct_plan_set_transform(b200dct_plan *plan, const float *t);
+/* Same, from a DEVICE pointer (what the reference's functions are handed); does one
+ * 256-byte synchronous copy. */
+int b200dct_plan_set_transform_device(b200dct_plan *plan, const void *d_t);
+
+/* Bit (row*8+col) set <=> that quantised coefficient is kept; dropped ones are +0.0f.
+ * b200dct_zigzag_mask(k) keeps the first k coefficients in JPEG zig-zag order
+ * (README.md:63 of the reference: "retaining 6..10 coefficients"). */
+int b200dct_plan_set_keep_mask(b200dct_plan *plan, uint64_t mask);
+uint64_t b200dct_zigzag_mask(int k);
+
+int b200dct_plan_set_path(b200dct_plan *plan, b200dct_path path);
+/* 1 if the plan's T is Haweel's matrix (sparse kernels), 0 if dense. */
+int b200dct_plan_is_sparse(const b200dct_plan *plan);
+
+/* Forward: coef = round((T.(img-128).T^T) / Q) [masked].  img: F32 or U8; coef: F32 or I16.
+ * If shifted_or_null is non-NULL (F32, same pitch as img; may alias img) it receives
+ * img-128, the side effect the reference leaves in its input (main_newAppr.cu:273). */
+int b200dct_forward(const b200dct_plan *plan,
+                    const void *img, b200dct_dtype img_dt, size_t img_pitch,
+                    void *coef, b200dct_dtype coef_dt, size_t coef_pitch,
+                    void *shifted_or_null,
+                    int H, int W, void *stream);
+
+/* Inverse: img = T^T.(coef*Q).T + 128.  coef: F32 or I16; img: F32 (not clamped, as the
+ * reference) or U8 (clamp to [0,255] then truncate, utils.cu:21). */
+int b200dct_inverse(const b200dct_plan *plan,
+                    const void *coef, b200dct_dtype coef_dt, size_t coef_pitch,
+                    void *img, b200dct_dtype img_dt, size_t img_pitch,
+                    int H, int W, void *stream);
+
+/* Fused forward+inverse in one HBM round trip (the headline path).  coef_or_null
+ * optionally receives the quantised coefficients as well. */
+int b200dct_roundtrip(const b200dct_plan *plan,
+                      const void *img, b200dct_dtype in_dt, size_t in_pitch,
+                      void *out, b200dct_dtype out_dt, size_t out_pitch,
+                      void *coef_or_null, b200dct_dtype coef_dt, size_t coef_pitch,
+                      int H, int W, void *stream);
+
+/* Host-buffer round trip: what the reference's main() does around its two calls
+ * (cudaMalloc, H2D, dct, idct, D2H: main_newAppr.cu:88-124), as one call on the current
+ * device.  h_in/h_out are HOST pointers (pinned or pageable), tightly packed rows.
+ * Internally the image is cut into block-row chunks that are copied, transformed and
+ * copied back on rotating streams so H2D, kernel and D2H overlap.  Synchronous. */
+int b200dct_roundtrip_host(const b200dct_plan *plan,
+                           const void *h_in, b200dct_dtype in_dt,
+                           void *h_out, b200dct_dtype out_dt,
+                           int H, int W);
+
+/* Sum of squared error and signal energy between two device images (same dtype,
+ * F32 or U8), accumulated in double: MSE = sse/N, PEEN% = 100*sqrt(sse/energy)
+ * (the definitions recovered from README.md:67-68 of the reference).
+ * d_acc: device pointer to 2 doubles {sse, energy}; the call ADDS into it. */
+int b200dct_metrics_accumulate(const void *ref_img, const void *test_img, b200dct_dtype dt,
+                               size_t pitch, int H, int W, double *d_acc, void *stream);
+
+/* Self-test of the kernels' constant-divisor division: sweeps the float bit patterns
+ * [first, first+count) as dividends against __fdiv_rn (the reference's div.rn.f32,
+ * utils_kernels.cu:42) for divisor d.  ADDS into d_out2 (device, 2 x uint64):
+ * [0] quotients whose bits differ, [1] quantised values roundf(q) that differ. */
+int b200dct_selftest_division(float d, unsigned long long first, unsigned long long count,
+                              unsigned long long *d_out2, void *stream);
+
+/* How many kernels the last call on this thread launched (for bench accounting). */
+int b200dct_last_launch_count(void);
+/* Name of the kernel family the last call on this thread used: "tma" or "direct". */
+const char *b200dct_last_path(void);
+
+const char *b200dct_error_string(int err);
+int b200dct_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DCT_H */

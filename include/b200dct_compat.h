@@ -1,0 +1,74 @@
+/*
+ * b200dct_compat.h -- the reference's own host entry points, re-implemented on the
+ * B200 kernels (libb200dct_compat.so).  A program written against the reference links
+ * this library instead of main_*.o's definitions and keeps calling the same functions:
+ * same names, same C++ signatures (hence the same mangled symbols), same argument
+ * meaning -- note the (height, width) order -- and the same observable side effects:
+ *
+ *   - all pointers are caller-owned DEVICE pointers; T is 64 floats on the device
+ *     (main_newAppr.cu:88-95);
+ *   - dct_*: the input image is left holding image-128 (sub_matrix_scalar runs in place,
+ *     main_newAppr.cu:273; main_cublass_2.cu:222);
+ *   - cublasDCTv2's idct_all_blocks(float*,...) leaves its INPUT dequantised
+ *     (multiply_matrices in place, main_cublass_2.cu:282);
+ *   - each call is synchronous and prints "DCT (w,h): t ms" / "IDCT (w,h): t ms" with the
+ *     device time of its kernels (main_newAppr.cu:267-287,308-328);
+ *   - errors print "<cuda error string> : <line>" and exit(EXIT_FAILURE), the CHECK_CUDA
+ *     contract (main_newAppr.cu:9-17).
+ *
+ * Differences that cannot be hidden: the reference's quantisation table is a TU-local
+ * __constant__ symbol the caller fills (main_newAppr.cu:19,70) which a separately linked
+ * library cannot see, so Q is set with b200dct_compat_set_quant() (default: the JPEG
+ * luminance table, the only value the reference ever uses); the cuBLAS handle is
+ * accepted and ignored (no cuBLAS anywhere); rectangular images work in every variant
+ * (fastApprDCT and both cuBLAS variants are square-only, main_fastAppr.cu:327,
+ * main_cublass.cu:211).
+ */
+#ifndef B200DCT_COMPAT_H
+#define B200DCT_COMPAT_H
+
+#include "b200dct.h"
+
+#ifdef __cplusplus
+
+#ifndef CUBLAS_V2_H_
+struct cublasContext;
+typedef struct cublasContext *cublasHandle_t;
+#endif
+
+/* HpApprDCT and fastApprDCT (main_newAppr.cu:23-24, main_fastAppr.cu:22-23) */
+void dct_all_blocks_cuda(float *image_matrix, const int img_height, const int img_width,
+                         const float *transform_matrix, float *result);
+void idct_all_blocks_cuda(const float *image_matrix, const int img_height, const int img_width,
+                          const float *transform_matrix, float *result);
+
+/* cublasDCT (main_cublass.cu:36-37) and cublasDCTv2 (main_cublass_2.cu:36-37) */
+void dct_all_blocks(float *image_matrix, int img_height, int img_width, const float *transform_matrix,
+                    float *result, cublasHandle_t handle);
+void idct_all_blocks(const float *image_matrix, int img_height, int img_width, const float *transform_matrix,
+                     float *result, cublasHandle_t handle);
+void idct_all_blocks(float *image_matrix, int img_height, int img_width, const float *transform_matrix,
+                     float *result, cublasHandle_t handle);
+
+extern "C" {
+#endif
+
+/* Replaces cudaMemcpyToSymbol(const_quant_matrix, q, ...) (main_newAppr.cu:70). q: 64 host floats. */
+int b200dct_compat_set_quant(const float *q);
+/* Retained-coefficient mask applied by dct_* (all ones by default). */
+int b200dct_compat_set_keep_mask(uint64_t mask);
+/* side_effects: 1 (default) reproduces the in-place input mutations listed above, 0 skips
+ * them (saves 4 B/px of traffic).  print_timing: 1 (default) prints the reference's lines. */
+void b200dct_compat_set_options(int side_effects, int print_timing);
+/* Device milliseconds of the kernels of the last dct_ / idct_ call on this thread. */
+float b200dct_compat_last_ms(void);
+
+/* C-callable aliases of the C++ entry points, for FFI users (ctypes/cgo/JNI). */
+void b200dct_compat_dct(float *image, int H, int W, const float *d_T, float *result);
+void b200dct_compat_idct(const float *coef, int H, int W, const float *d_T, float *result);
+void b200dct_compat_idct_inplace_dequant(float *coef, int H, int W, const float *d_T, float *result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DCT_COMPAT_H */

