@@ -25,7 +25,8 @@ class B200DCTError(RuntimeError):
 
 
 def lib_path(name: str = "libb200dct.so") -> str:
-    return os.path.join(_HERE, name)
+    # B200DCT_LIB_DIR: developer override used to A/B experimental builds of the library
+    return os.path.join(os.environ.get("B200DCT_LIB_DIR", _HERE), name)
 
 
 _lib = None

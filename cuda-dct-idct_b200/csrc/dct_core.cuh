@@ -188,8 +188,15 @@ __device__ __forceinline__ void row_pass(const float (&m)[8], float (&o)[8], con
             sfor<8>([&](auto i) {
                 if constexpr (TP::is_static) {
                     constexpr float ta = TP::at(xa, IC(i)), tb = TP::at(xb, IC(i));
-                    if constexpr (ta != 0.0f || tb != 0.0f)
-                        acc = ffma2(bc(m[IC(i)]), make_float2(ta, tb), acc);
+                    if constexpr (ta != 0.0f || tb != 0.0f) {
+                        // fma(m,t,c) == fma(-m,-t,c) exactly: normalise the sign of the constant
+                        // pair so that only {a,-a},{h,-h},{p,q},{q,-p},{s,-s} ever need registers
+                        // (equal halves are broadcast immediates); the sign goes onto m.
+                        constexpr bool neg = ta < 0.0f || (ta == 0.0f && tb < 0.0f);
+                        constexpr float na = neg ? -ta : ta, nb = neg ? -tb : tb;
+                        const float mm = neg ? -m[IC(i)] : m[IC(i)];
+                        acc = ffma2(bc(mm), make_float2(na, nb), acc);
+                    }
                 } else {
                     acc = ffma2(bc(m[IC(i)]), tp.at2(xa, IC(i)), acc);
                 }

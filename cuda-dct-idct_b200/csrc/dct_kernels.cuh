@@ -204,6 +204,9 @@ struct TmaParams {
     uint32_t ntiles;
     int coef_dt;          // DT_F32 / DT_I16
     int has_coef;         // RT: also emit the coefficient plane
+    // Dynamic tile scheduler: {next ticket, finished warps}, both 0 at launch and reset to 0
+    // by the last warp to leave; NULL = static round-robin (used under stream capture).
+    uint32_t *sched;
     CommonParams cp;
 };
 
@@ -319,8 +322,27 @@ __device__ __forceinline__ uint32_t tile_bytes()
     return DT == DT_F32 ? 8192u : (DT == DT_I16 ? 4096u : 2048u);
 }
 
+// Register budget of the persistent kernel: at most B200DCT_TMA_CTA_THREADS threads per
+// CTA, one CTA per SM.  Measured on B200 at 8192^2 f32 (gpurun_out/sweep.log, round 1):
+// 4 warps 119 us, 6: 96, 7: 90, 8: 84.0, 9: 84.0, then a cliff -- 10: 113, 12: 117, 14: 118
+// (more than ~21 MB of tile buffers in flight chip-wide thrashes; u8 tiles, 4x smaller,
+// show no cliff).  8 warps = 2 per scheduler is enough because every thread carries 64
+// independent FMA chains.
+#ifndef B200DCT_TMA_CTA_THREADS
+#define B200DCT_TMA_CTA_THREADS 288
+#endif
+#ifndef B200DCT_TMA_DEFAULT_WARPS
+#define B200DCT_TMA_DEFAULT_WARPS 8
+#endif
+#ifdef B200DCT_TMA_MAXNREG
+#define B200DCT_TMA_BOUNDS __maxnreg__(B200DCT_TMA_MAXNREG)
+#else
+#define B200DCT_TMA_BOUNDS __launch_bounds__(B200DCT_TMA_CTA_THREADS, 1)
+#endif
+constexpr int TMA_MAX_WARPS = B200DCT_TMA_CTA_THREADS / 32;
+
 template <int MODE, bool SPARSE, int QMODE, int PIX>
-__global__ void __launch_bounds__(448, 1) k_tma(const __grid_constant__ TmaParams P)
+__global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
 {
     extern __shared__ uint8_t smem_raw[];
     // 1 KiB alignment: the 128B swizzle pattern is a function of address bits 7..9
@@ -332,11 +354,21 @@ __global__ void __launch_bounds__(448, 1) k_tma(const __grid_constant__ TmaParam
     const uint32_t bar = smem_base + nwarps * WARP_SMEM_BYTES + warp * 8;
     const uint32_t off0 = f32_tile_off0(lane);
 
-    // tiles are dealt round-robin over all resident warps (CTA-minor), so the warps that
-    // are in flight at any moment cover one contiguous window of the image
+    // Tiles are handed out by a global ticket counter (the two dies / far and near L2
+    // slices make SMs progress at different speeds; with a static split the slow SMs set the
+    // kernel time while the fast ones idle).  Tickets are fetched one tile ahead so the
+    // atomic's latency hides behind the TMA wait.  Without a counter: static round-robin,
+    // CTA-minor, so the warps in flight cover one contiguous window of the image.
     const uint32_t stride = gridDim.x * nwarps;
-    uint32_t tile = warp * gridDim.x + blockIdx.x;
-
+    uint32_t *const sched = P.sched;
+    auto next_ticket = [&](uint32_t cur) -> uint32_t {
+        uint32_t t = 0;
+        if (lane == 0) t = sched ? atomicAdd(&sched[0], 1u) : cur + stride;
+        return t; // valid in lane 0 only; broadcast by the caller
+    };
+    uint32_t tile = 0;
+    if (lane == 0) tile = sched ? atomicAdd(&sched[0], 1u) : warp * gridDim.x + blockIdx.x;
+    tile = __shfl_sync(0xffffffffu, tile, 0);
     const bool in_is_f32 = (MODE == MODE_INV) ? (P.coef_dt == DT_F32) : (PIX == DT_F32);
     const uint32_t in_bytes = (MODE == MODE_INV) ? (P.coef_dt == DT_F32 ? 8192u : 4096u) : tile_bytes<PIX>();
 
@@ -355,8 +387,9 @@ __global__ void __launch_bounds__(448, 1) k_tma(const __grid_constant__ TmaParam
     __syncwarp();
 
     uint32_t parity = 0;
-    for (; tile < P.ntiles; tile += stride) {
+    while (tile < P.ntiles) {
         const int ty = (int)(tile / P.tiles_x), tx = (int)(tile - (uint32_t)ty * P.tiles_x);
+        const uint32_t next_l0 = next_ticket(tile);
         mbar_wait(bar, parity);
         parity ^= 1;
 
@@ -372,8 +405,7 @@ __global__ void __launch_bounds__(448, 1) k_tma(const __grid_constant__ TmaParam
             sfor<8>([&](auto r) { unpack_u8_shifted(lds64u(in_buf + IC(r) * 256 + lane * 8), p[IC(r)]); });
         }
         // every lane has consumed its part of in_buf: re-arm it with the next tile
-        __syncwarp();
-        const uint32_t next = tile + stride;
+        const uint32_t next = __shfl_sync(0xffffffffu, next_l0, 0); // also the warp-wide sync
         if (lane == 0 && next < P.ntiles) issue_load(next);
 
         auto put_coef_tile = [&](const CUtensorMap *map, float2 (&c)[8][4]) {
@@ -414,8 +446,20 @@ __global__ void __launch_bounds__(448, 1) k_tma(const __grid_constant__ TmaParam
                 tma_store_commit();
             }
         }
+        tile = next;
     }
-    if (lane == 0) tma_store_wait_read();
+    if (lane == 0) {
+        tma_store_wait_read();
+        if (sched) {
+            // every warp draws exactly one losing ticket; the last one out re-zeroes the counters
+            __threadfence();
+            if (atomicAdd(&sched[1], 1u) == stride - 1) {
+                sched[0] = 0;
+                sched[1] = 0;
+                __threadfence();
+            }
+        }
+    }
 }
 
 } // namespace b200dct

@@ -15,6 +15,13 @@ namespace b200dct {
 
 cudaError_t INST_NAME(int mode, int qmode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s)
 {
+#ifdef B200DCT_FAST_BUILD /* experiment builds: headline kernels only */
+#if INST_SPARSE
+    B200_TMA_CASE(MODE_RT, Q_IMM, DT_F32)
+    B200_TMA_CASE(MODE_RT, Q_IMM, DT_U8)
+#endif
+    return cudaErrorInvalidValue;
+#endif
 #if INST_SPARSE
     B200_TMA_MODES(Q_IMM, DT_F32)
     B200_TMA_MODES(Q_IMM, DT_U8)

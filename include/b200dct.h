@@ -150,7 +150,8 @@ int b200dct_metrics_accumulate(const void *ref_img, const void *test_img, b200dc
 /* Self-test of the kernels' constant-divisor division: sweeps the float bit patterns
  * [first, first+count) as dividends against __fdiv_rn (the reference's div.rn.f32,
  * utils_kernels.cu:42) for divisor d.  ADDS into d_out2 (device, 2 x uint64):
- * [0] quotients whose bits differ, [1] quantised values roundf(q) that differ. */
+ * [0] quotients whose bits differ for |x| >= 2^-120, [1] quantised values roundf(q) that
+ * differ (x = -0.0f, which the transform cannot produce, is skipped). */
 int b200dct_selftest_division(float d, unsigned long long first, unsigned long long count,
                               unsigned long long *d_out2, void *stream);
 

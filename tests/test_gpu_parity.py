@@ -73,7 +73,7 @@ def test_forward_side_effect_shifted(dct, oracle):
 
 
 @pytest.mark.parametrize("path", ["tma", "direct"])
-@pytest.mark.parametrize("shape", [(8, 16), (256, 256), (72, 1040)])
+@pytest.mark.parametrize("shape", [(8, 32), (256, 256), (72, 1056)])
 def test_roundtrip_u8(dct, oracle, path, shape):
     img = oracle.rand_image_u8(*shape, 42)
     want_out, want_coef = oracle.roundtrip(img, want_coef=True)
@@ -88,6 +88,22 @@ def test_roundtrip_u8(dct, oracle, path, shape):
     assert np.array_equal(host(out), want_out) and np.array_equal(host(c16), want_coef.astype(np.int16))
     c = dct.forward(dev(img), plan=plan)
     assert np.array_equal(bits(host(c)), bits(want_coef))
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (8, 16), (72, 1040), (16, 24)])
+def test_auto_path_falls_back_to_direct_on_narrow_or_odd_widths(dct, oracle, shape):
+    """W % 32 != 0 cannot be tiled by the f32 TMA view: AUTO silently uses the direct kernels,
+    forcing TMA is an error (never a wrong result)."""
+    img8 = oracle.rand_image_u8(*shape, 42)
+    img = img8.astype(np.float32)
+    want_out, want_coef = oracle.roundtrip(img, want_coef=True)
+    coef = torch.empty(shape, dtype=torch.float32, device="cuda")
+    out = dct.roundtrip(dev(img), coef=coef)
+    assert dct.api.last_path() == "direct"
+    assert np.array_equal(bits(host(out)), bits(want_out)) and np.array_equal(bits(host(coef)), bits(want_coef))
+    assert np.array_equal(host(dct.roundtrip(dev(img8))), oracle.to_u8(want_out))
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(dev(img), plan=dct.Plan(path=2))
 
 
 @pytest.mark.parametrize("path", ["tma", "direct"])
