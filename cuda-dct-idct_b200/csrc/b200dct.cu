@@ -200,6 +200,12 @@ static bool make_map(CUtensorMap *map, const void *ptr, int dt, size_t pitch, in
     encode_tiled_fn enc = get_encode();
     if (!enc) return false;
     CUresult r;
+    static int promo_env = -1; // developer knob: B200DCT_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B
+    if (promo_env < 0) {
+        const char *e = getenv("B200DCT_TMA_L2PROMO");
+        promo_env = (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 3;
+    }
+    const CUtensorMapL2promotion promo = (CUtensorMapL2promotion)promo_env;
     if (dt == DT_F32) {
         // {32 floats, W/32 segments, H rows}; box = 8 rows x 8 segments x 128 B, 128B swizzle
         cuuint64_t dims[3] = {32, (cuuint64_t)(W / 32), (cuuint64_t)H};
@@ -207,7 +213,7 @@ static bool make_map(CUtensorMap *map, const void *ptr, int dt, size_t pitch, in
         cuuint32_t box[3] = {32, 8, 8};
         cuuint32_t es[3] = {1, 1, 1};
         r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr), dims, strides, box, es,
-                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H};
@@ -216,7 +222,7 @@ static bool make_map(CUtensorMap *map, const void *ptr, int dt, size_t pitch, in
         cuuint32_t es[2] = {1, 1};
         r = enc(map, dt == DT_U8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 2,
                 const_cast<void *>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     return r == CUDA_SUCCESS;
 }
