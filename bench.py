@@ -357,6 +357,7 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     m.dist.barrier()
+    m.dist.shutdown()
     return 0
 
 

@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
         L.b200dct_roundtrip.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp]
         L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
         L.b200dct_metrics_accumulate.argtypes = [vp, vp, i, sz, i, i, vp, vp]
+        L.b200dct_time_calls.argtypes = [vp, i, vp, i, sz, vp, i, sz, vp, i, sz, i, i, i, C.POINTER(C.c_float), vp]
         L.b200dct_selftest_division.argtypes = [C.c_float, C.c_ulonglong, C.c_ulonglong, vp, vp]
         L.b200dct_last_launch_count.restype = i
         L.b200dct_last_path.restype = C.c_char_p
@@ -278,6 +279,23 @@ def metrics(ref_img, test_img, stream=None):
     sse, energy = acc.tolist()
     n = H * W
     return sse / n, (100.0 * (sse / energy) ** 0.5 if energy > 0 else 0.0)
+
+
+def time_calls(which: str, a, b, c=None, plan: Plan | None = None, iters: int = 100, stream=None) -> float:
+    """Average device ms of `iters` back-to-back calls issued from C (b200dct_time_calls).
+    which: "roundtrip" (a -> b [, c = coefficient plane]), "forward", "inverse", or
+    "split" (forward a -> c, inverse c -> b)."""
+    import torch
+
+    code = {"roundtrip": 0, "forward": 1, "inverse": 2, "split": 3}[which]
+    ap, adt, apitch, H, W = _plane(a)
+    bp, bdt, bpitch, _, _ = _plane(b)
+    cp, cdt, cpitch = (None, F32, 0) if c is None else _plane(c)[:3]
+    ms = C.c_float()
+    with torch.cuda.device(a.device):
+        _check(lib().b200dct_time_calls(_plan(plan)._h, code, ap, adt, apitch, bp, bdt, bpitch, cp, cdt, cpitch,
+                                        H, W, int(iters), C.byref(ms), _stream(stream)))
+    return float(ms.value)
 
 
 def last_launch_count() -> int:

@@ -275,6 +275,7 @@ uint32_t *sched_slot()
 
 static bool tma_dynamic = true; // env B200DCT_TMA_STATIC=1 forces the static tile split
 static int tma_warps = B200DCT_TMA_DEFAULT_WARPS; // warps per CTA of the persistent kernel (env B200DCT_TMA_WARPS, 1..TMA_MAX_WARPS)
+static int tma_max_run = 2;                       // env B200DCT_TMA_RUN: longest run of tiles per claim
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
 
 static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,
@@ -302,7 +303,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // f32/i16 plane); all-u8 round trips move 2 B/px, are FP32-pipe bound, and run faster on
     // the direct family's 16 resident warps per SM (69.7 vs 84 us at 8192^2, round 1).
     const size_t bytes_per_px = elem_size(in.dt) + elem_size(out.dt) + (coef.ptr ? elem_size(coef.dt) : 0);
-    const bool prefer_tma = pl->path == B200DCT_PATH_TMA || bytes_per_px >= 4;
+    // Dense T (32 FMA/px instead of 22) is FP32-pipe bound as well: direct 98 us vs TMA 105 us.
+    const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse);
     bool use_tma = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && get_encode() != nullptr &&
                    tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
                    (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
@@ -313,6 +315,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         std::call_once(once, [] {
             const char *e = getenv("B200DCT_TMA_WARPS");
             if (e && atoi(e) >= 1 && atoi(e) <= TMA_MAX_WARPS) tma_warps = atoi(e);
+            const char *r = getenv("B200DCT_TMA_RUN");
+            if (r && atoi(r) >= 1 && atoi(r) <= 4096) tma_max_run = atoi(r);
             const char *g = getenv("B200DCT_TMA_GRID");
             if (g && atoi(g) >= 1) tma_grid = atoi(g);
             const char *d = getenv("B200DCT_TMA_STATIC");
@@ -329,6 +333,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.ntiles = (uint32_t)nt;
         P.coef_dt = coef_dt;
         P.has_coef = coef.ptr ? 1 : 0;
+
         // a captured launch may be replayed concurrently with anything: static split there
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (tma_dynamic && cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
@@ -339,6 +344,10 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         unsigned long long want = (nt + nw - 1) / nw;
         const unsigned long long gcap = (unsigned long long)(tma_grid > 0 ? tma_grid : di.sms);
         const int grid = (int)(want < gcap ? want : gcap);
+        // runs of tma_max_run tiles while more than two rounds of single tiles remain
+        P.run = (uint32_t)tma_max_run;
+        const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
+        P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
         cudaError_t e = pl->sparse ? launch_tma_sparse(mode, qm, pix, P, grid, nw * 32, smem, stream)
                                    : launch_tma_dense(mode, qm, pix, P, grid, nw * 32, smem, stream);
         if (e != cudaSuccess) return (int)e;
@@ -390,6 +399,49 @@ extern "C" int b200dct_roundtrip(const b200dct_plan *plan, const void *img, b200
                Plane{coef_or_null, (int)coef_dt, coef_pitch}, nullptr, H, W, (cudaStream_t)stream);
 }
 
+// Average device time of `iters` back-to-back identical calls, measured with CUDA events on
+// `stream` from C (no interpreter between launches).  which: 0 roundtrip(a -> b [,c = coef]),
+// 1 forward(a -> b), 2 inverse(a -> b), 3 forward(a -> c) then inverse(c -> b).
+extern "C" int b200dct_time_calls(const b200dct_plan *plan, int which, const void *a, b200dct_dtype a_dt, size_t a_pitch,
+                                  void *b, b200dct_dtype b_dt, size_t b_pitch, void *c, b200dct_dtype c_dt,
+                                  size_t c_pitch, int H, int W, int iters, float *ms_per_iter, void *stream)
+{
+    if (!ms_per_iter || iters < 1) return B200DCT_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return B200DCT_ERR_NODEVICE;
+    int rc = B200DCT_OK, launches = 0;
+    auto once = [&]() -> int {
+        switch (which) {
+        case 0: return b200dct_roundtrip(plan, a, a_dt, a_pitch, b, b_dt, b_pitch, c, c_dt, c_pitch, H, W, stream);
+        case 1: return b200dct_forward(plan, a, a_dt, a_pitch, b, b_dt, b_pitch, nullptr, H, W, stream);
+        case 2: return b200dct_inverse(plan, a, a_dt, a_pitch, b, b_dt, b_pitch, H, W, stream);
+        case 3: {
+            int r = b200dct_forward(plan, a, a_dt, a_pitch, c, c_dt, c_pitch, nullptr, H, W, stream);
+            return r ? r : b200dct_inverse(plan, c, c_dt, c_pitch, b, b_dt, b_pitch, H, W, stream);
+        }
+        default: return B200DCT_ERR_ARG;
+        }
+    };
+    for (int i = 0; i < 3 && rc == B200DCT_OK; i++) rc = once(); // warm-up
+    if (rc == B200DCT_OK) {
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters && rc == B200DCT_OK; i++) {
+            rc = once();
+            launches += tl_launches * (which == 3 ? 2 : 1);
+        }
+        cudaEventRecord(e1, s);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (rc == B200DCT_OK && e != cudaSuccess) rc = (int)e;
+        float ms = 0.0f;
+        if (rc == B200DCT_OK && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) *ms_per_iter = ms / (float)iters;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    tl_launches = launches;
+    return rc;
+}
+
 // ------------------------------------------------------------------ host-buffer round trip
 // Per-thread, per-device grow-only workspace: NCHUNK stream slots, each with an input
 // and an output chunk buffer.  Chunks are block-row stripes, so every chunk is itself a
@@ -429,8 +481,14 @@ extern "C" int b200dct_roundtrip_host(const b200dct_plan *plan, const void *h_in
     if (cudaGetDevice(&dev) != cudaSuccess) return B200DCT_ERR_NODEVICE;
     const size_t es = elem_size((int)in_dt);
     const size_t row = (size_t)W * es;
-    // ~16 MiB chunks, at least 8 rows, whole block-rows
-    long long rows = (long long)((16u << 20) / row) & ~7ll;
+    // ~16 MiB chunks (env B200DCT_HOST_CHUNK_MB; measured best of 2..32 MiB on B200, round 1), at least 8 rows, whole block-rows: small
+    // enough that the un-overlapped first H2D / last D2H are a few percent of the transfer
+    static int chunk_mb = 0;
+    if (!chunk_mb) {
+        const char *e = getenv("B200DCT_HOST_CHUNK_MB");
+        chunk_mb = (e && atoi(e) >= 1 && atoi(e) <= 1024) ? atoi(e) : 16;
+    }
+    long long rows = (long long)(((size_t)chunk_mb << 20) / row) & ~7ll;
     if (rows < 8) rows = 8;
     if (rows > H) rows = H;
     const size_t chunk_bytes = (size_t)rows * row;

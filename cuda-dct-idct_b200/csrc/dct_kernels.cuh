@@ -207,6 +207,8 @@ struct TmaParams {
     // Dynamic tile scheduler: {next ticket, finished warps}, both 0 at launch and reset to 0
     // by the last warp to leave; NULL = static round-robin (used under stream capture).
     uint32_t *sched;
+    uint32_t run;         // tiles per ticket for the first run_tickets tickets, then 1
+    uint32_t run_tickets;
     CommonParams cp;
 };
 
@@ -323,13 +325,14 @@ __device__ __forceinline__ uint32_t tile_bytes()
 }
 
 // Register budget of the persistent kernel: at most B200DCT_TMA_CTA_THREADS threads per
-// CTA, one CTA per SM.  Measured on B200 at 8192^2 f32 (gpurun_out/sweep.log, round 1):
-// 4 warps 119 us, 6: 96, 7: 90, 8: 84.0, 9: 84.0, then a cliff -- 10: 113, 12: 117, 14: 118
-// (more than ~21 MB of tile buffers in flight chip-wide thrashes; u8 tiles, 4x smaller,
-// show no cliff).  8 warps = 2 per scheduler is enough because every thread carries 64
-// independent FMA chains.
+// CTA, one CTA per SM.  Measured on B200 at 8192^2 f32 (profiles/r01_tma_warps_sweep.txt):
+// 4 warps 119 us, 6: 96, 7: 90, 8: 84.0, 9: 84.0.  8 warps = 2 per scheduler is enough
+// because every thread carries 64 independent FMA chains.  (With single-tile tickets more
+// warps, or a working set above ~1 GiB, collapsed to 113-118 us: the TMA path's address
+// translation thrashes when every SM touches every 2 MiB page; runs of 2 consecutive tiles
+// per ticket removed that -- profiles/r01_tma_run_scheduler.txt.)
 #ifndef B200DCT_TMA_CTA_THREADS
-#define B200DCT_TMA_CTA_THREADS 288
+#define B200DCT_TMA_CTA_THREADS 256
 #endif
 #ifndef B200DCT_TMA_DEFAULT_WARPS
 #define B200DCT_TMA_DEFAULT_WARPS 8
@@ -354,20 +357,28 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     const uint32_t bar = smem_base + nwarps * WARP_SMEM_BYTES + warp * 8;
     const uint32_t off0 = f32_tile_off0(lane);
 
-    // Tiles are handed out by a global ticket counter (the two dies / far and near L2
-    // slices make SMs progress at different speeds; with a static split the slow SMs set the
-    // kernel time while the fast ones idle).  Tickets are fetched one tile ahead so the
-    // atomic's latency hides behind the TMA wait.  Without a counter: static round-robin,
-    // CTA-minor, so the warps in flight cover one contiguous window of the image.
+    // Dynamic tile scheduler.  The two dies / far and near L2 slices make SMs progress at
+    // different speeds: with a static split the slow SMs set the kernel time while the fast
+    // ones idle (17 % of the SM-cycles in ncu, round 1).  Warps therefore draw tickets from
+    // a global counter (one atomicAdd per claim, fetched one tile ahead so its latency hides
+    // behind the TMA wait).  The first P.run_tickets tickets are worth a RUN of P.run
+    // consecutive tiles each (consecutive tiles share their image rows, hence their 2 MiB
+    // pages: the TMA unit's address translation is what collapses when every SM wanders
+    // over every page of a multi-GiB working set); the remaining tickets are worth one tile
+    // each, so the tail of the kernel stays one tile long.  Without a counter (stream
+    // capture): static round-robin.
     const uint32_t stride = gridDim.x * nwarps;
     uint32_t *const sched = P.sched;
-    auto next_ticket = [&](uint32_t cur) -> uint32_t {
-        uint32_t t = 0;
-        if (lane == 0) t = sched ? atomicAdd(&sched[0], 1u) : cur + stride;
-        return t; // valid in lane 0 only; broadcast by the caller
+    uint32_t run_left = 0; // lane 0: tiles still owned after the current one
+    auto claim_next = [&](uint32_t cur) -> uint32_t { // lane 0 only; returns the next tile (>= ntiles: none)
+        if (!sched) return cur + stride;
+        if (run_left) { run_left--; return cur + 1; }
+        const uint32_t t = atomicAdd(&sched[0], 1u);
+        if (t < P.run_tickets) { run_left = P.run - 1; return t * P.run; }
+        return P.run_tickets * P.run + (t - P.run_tickets); // may be >= ntiles: the losing ticket
     };
     uint32_t tile = 0;
-    if (lane == 0) tile = sched ? atomicAdd(&sched[0], 1u) : warp * gridDim.x + blockIdx.x;
+    if (lane == 0) tile = sched ? claim_next(0) : warp * gridDim.x + blockIdx.x;
     tile = __shfl_sync(0xffffffffu, tile, 0);
     const bool in_is_f32 = (MODE == MODE_INV) ? (P.coef_dt == DT_F32) : (PIX == DT_F32);
     const uint32_t in_bytes = (MODE == MODE_INV) ? (P.coef_dt == DT_F32 ? 8192u : 4096u) : tile_bytes<PIX>();
@@ -389,7 +400,8 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     uint32_t parity = 0;
     while (tile < P.ntiles) {
         const int ty = (int)(tile / P.tiles_x), tx = (int)(tile - (uint32_t)ty * P.tiles_x);
-        const uint32_t next_l0 = next_ticket(tile);
+        uint32_t next_l0 = 0;
+        if (lane == 0) next_l0 = claim_next(tile);
         mbar_wait(bar, parity);
         parity ^= 1;
 
@@ -451,7 +463,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     if (lane == 0) {
         tma_store_wait_read();
         if (sched) {
-            // every warp draws exactly one losing ticket; the last one out re-zeroes the counters
+            // every warp ends on exactly one losing ticket; the last warp out re-zeroes both counters
             __threadfence();
             if (atomicAdd(&sched[1], 1u) == stride - 1) {
                 sched[0] = 0;

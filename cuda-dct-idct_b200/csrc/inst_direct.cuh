@@ -15,7 +15,7 @@ cudaError_t INST_NAME(int mode, int qmode, int pix, const DirectParams &P, dim3 
 {
 #ifdef B200DCT_FAST_BUILD /* experiment builds: headline kernels only */
 #if INST_SPARSE
-    B200_DIRECT_CASE(MODE_RT, Q_IMM, DT_F32)
+    B200_DIRECT_MODES(Q_IMM, DT_F32)
     B200_DIRECT_CASE(MODE_RT, Q_IMM, DT_U8)
 #endif
     return cudaErrorInvalidValue;

@@ -17,7 +17,7 @@ cudaError_t INST_NAME(int mode, int qmode, int pix, const TmaParams &P, int grid
 {
 #ifdef B200DCT_FAST_BUILD /* experiment builds: headline kernels only */
 #if INST_SPARSE
-    B200_TMA_CASE(MODE_RT, Q_IMM, DT_F32)
+    B200_TMA_MODES(Q_IMM, DT_F32)
     B200_TMA_CASE(MODE_RT, Q_IMM, DT_U8)
 #endif
     return cudaErrorInvalidValue;

@@ -33,6 +33,13 @@ def init(backend: str | None = None):
     return rank, local_rank, world
 
 
+def shutdown():
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def barrier():
     import torch.distributed as dist
 

@@ -147,6 +147,17 @@ int b200dct_roundtrip_host(const b200dct_plan *plan,
 int b200dct_metrics_accumulate(const void *ref_img, const void *test_img, b200dct_dtype dt,
                                size_t pitch, int H, int W, double *d_acc, void *stream);
 
+/* Measurement helper: average device milliseconds of `iters` back-to-back identical calls
+ * (CUDA events on `stream`, launched from C so no interpreter sits between launches).
+ * which: 0 roundtrip(a -> b, optional coefficient plane c), 1 forward(a -> b),
+ * 2 inverse(a -> b), 3 forward(a -> c) followed by inverse(c -> b) (the reference's
+ * two-call sequence, main_newAppr.cu:99,120). */
+int b200dct_time_calls(const b200dct_plan *plan, int which,
+                       const void *a, b200dct_dtype a_dt, size_t a_pitch,
+                       void *b, b200dct_dtype b_dt, size_t b_pitch,
+                       void *c, b200dct_dtype c_dt, size_t c_pitch,
+                       int H, int W, int iters, float *ms_per_iter, void *stream);
+
 /* Self-test of the kernels' constant-divisor division: sweeps the float bit patterns
  * [first, first+count) as dividends against __fdiv_rn (the reference's div.rn.f32,
  * utils_kernels.cu:42) for divisor d.  ADDS into d_out2 (device, 2 x uint64):
