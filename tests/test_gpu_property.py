@@ -1,0 +1,108 @@
+"""GPU property tests (hypothesis): random shapes, pitches, dtypes, masks, quantisers and
+kernel families against the CPU oracle, bit-exact; plus structural properties that hold at
+any size (block independence, batch == tall image, split == fused)."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy()
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(hb=st.integers(1, 12), wb=st.integers(1, 80), pad=st.sampled_from([0, 4, 8, 32, 100]),
+       u8=st.booleans(), path=st.sampled_from([0, 1]), k=st.sampled_from([64, 64, 10, 6, 1]),
+       qscale=st.sampled_from([1.0, 1.0, 2.0, 0.5, 0.37]), with_coef=st.sampled_from(["none", "f32", "i16"]),
+       seed=st.integers(0, 2 ** 16))
+def test_random_configurations_match_oracle(dct, oracle, hb, wb, pad, u8, path, k, qscale, with_coef, seed):
+    H, W = hb * 8, wb * 8
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, (H, W)).astype(np.uint8 if u8 else np.float32)
+    if not u8 and seed % 3 == 0:
+        img = (img + rng.random((H, W), dtype=np.float32)).astype(np.float32)   # non-integer pixels
+    Q = (oracle.jpeg_Q() * qscale).astype(np.float32)
+    keep = oracle.zigzag_mask(k)
+    want_out, want_coef = oracle.roundtrip(img, Q=Q, keep=keep, want_coef=True)
+    plan = dct.Plan(Q=Q, keep=keep, path=path)
+    pad_elems = pad if not u8 else pad * 4          # keep rows 16-byte aligned in both dtypes
+    big = torch.zeros(H, W + pad_elems, dtype=torch.uint8 if u8 else torch.float32, device="cuda")
+    big[:, :W] = torch.from_numpy(img).cuda()
+    outb = torch.full((H, W + pad_elems), 7, dtype=big.dtype, device="cuda")
+    coef = None
+    if with_coef != "none":
+        coef = torch.empty(H, W, dtype=torch.float32 if with_coef == "f32" else torch.int16, device="cuda")
+    dct.roundtrip(big[:, :W], out=outb[:, :W], coef=coef, plan=plan)
+    got = host(outb)
+    assert np.array_equal(got[:, :W] if u8 else bits(got[:, :W]), want_out if u8 else bits(want_out))
+    assert (got[:, W:] == 7).all()                   # padding columns untouched
+    if coef is not None:
+        assert np.array_equal(host(coef).astype(np.float32), want_coef)
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(hb=st.integers(2, 40), wb=st.sampled_from([4, 32, 36, 64, 128]), cut=st.integers(1, 39), seed=st.integers(0, 999))
+def test_stripes_batches_and_split_equal_fused(dct, hb, wb, cut, seed):
+    H, W = hb * 8, wb * 8
+    cut = min(cut, hb - 1) * 8
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    img = torch.randint(0, 256, (H, W), device="cuda", generator=g, dtype=torch.int32).float()
+    full = dct.roundtrip(img)
+    top, bottom = dct.roundtrip(img[:cut]), dct.roundtrip(img[cut:])
+    assert torch.equal(torch.cat([top, bottom]).view(torch.int32), full.view(torch.int32))
+    rec = dct.inverse(dct.forward(img))
+    assert torch.equal(rec.view(torch.int32), full.view(torch.int32))
+    rec16 = dct.inverse(dct.forward(img, coef_dtype=torch.int16))
+    assert torch.equal(rec16.view(torch.int32), full.view(torch.int32))
+    batch = img.view(2, H // 2, W) if (H // 8) % 2 == 0 else None
+    if batch is not None:
+        assert torch.equal(dct.roundtrip(batch).view(torch.int32).view(H, W), full.view(torch.int32))
+
+
+def test_time_calls_helper(dct, oracle):
+    img = torch.from_numpy(oracle.rand_image(256, 256, 42)).cuda()
+    out, coef = torch.empty_like(img), torch.empty_like(img)
+    for which in ("roundtrip", "forward", "inverse", "split"):
+        ms = dct.api.time_calls(which, img if which != "inverse" else coef, out, coef if which in ("roundtrip", "split") else None, iters=10)
+        assert 0 < ms < 5
+    dct.api.time_calls("split", img, out, coef, iters=3)
+    assert np.array_equal(bits(host(out)), bits(oracle.roundtrip(host(img))))
+
+
+def test_concurrent_streams_share_nothing(dct, oracle):
+    """Launches on different streams use different scheduler slots: results stay exact."""
+    imgs = [torch.from_numpy(oracle.rand_image(512, 512, s)).cuda() for s in range(4)]
+    outs = [torch.empty_like(x) for x in imgs]
+    streams = [torch.cuda.Stream() for _ in imgs]
+    torch.cuda.synchronize()
+    for rep in range(20):
+        for x, y, s in zip(imgs, outs, streams):
+            dct.roundtrip(x, out=y, stream=s)
+    torch.cuda.synchronize()
+    for i, (x, y) in enumerate(zip(imgs, outs)):
+        assert np.array_equal(bits(host(y)), bits(oracle.roundtrip(oracle.rand_image(512, 512, i))))
+
+
+def test_cuda_graph_capture_uses_static_schedule(dct, oracle):
+    img = torch.from_numpy(oracle.rand_image(512, 512, 3)).cuda()
+    out = torch.empty_like(img)
+    dct.roundtrip(img, out=out)          # warm-up outside capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.graph(g, stream=s):
+        dct.roundtrip(img, out=out, stream=torch.cuda.current_stream())
+    out.zero_()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(host(out)), bits(oracle.roundtrip(oracle.rand_image(512, 512, 3))))
