@@ -22,6 +22,7 @@ from .api import (  # noqa: F401
     metrics,
     roundtrip,
     roundtrip_host,
+    roundtrip_with_metrics,
     zigzag_mask,
 )
 from . import api, dist  # noqa: F401
@@ -31,5 +32,5 @@ from .stripes import stripe_rows  # noqa: F401
 __all__ = [
     "ALL_COEFFS", "B200DCTError", "Plan", "build", "dct_all_blocks", "dct_all_blocks_cuda", "forward",
     "idct_all_blocks", "idct_all_blocks_cuda", "inverse", "lib", "lib_path", "metrics", "roundtrip",
-    "roundtrip_host", "stripe_rows", "zigzag_mask",
+    "roundtrip_host", "roundtrip_with_metrics", "stripe_rows", "zigzag_mask",
 ]

@@ -59,6 +59,9 @@ def lib() -> C.CDLL:
         L.b200dct_forward.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, i, vp]
         L.b200dct_inverse.argtypes = [vp, vp, i, sz, vp, i, sz, i, i, vp]
         L.b200dct_roundtrip.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp]
+        L.b200dct_metrics_workspace_bytes.argtypes = [i, i]
+        L.b200dct_metrics_workspace_bytes.restype = sz
+        L.b200dct_roundtrip_metrics.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp, vp, sz, vp]
         L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
         L.b200dct_metrics_accumulate.argtypes = [vp, vp, i, sz, i, i, vp, vp]
         L.b200dct_time_calls.argtypes = [vp, i, vp, i, sz, vp, i, sz, vp, i, sz, i, i, i, C.POINTER(C.c_float), vp]
@@ -235,6 +238,27 @@ def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None):
         _check(lib().b200dct_roundtrip(_plan(plan)._h, ip, idt, ipitch, op, odt, opitch, cp, cdt, cpitch, H, W,
                                        _stream(stream)))
     return out
+
+
+def roundtrip_with_metrics(img, out=None, coef=None, plan: Plan | None = None, stream=None):
+    """Fused round trip that also returns (MSE, PEEN%, non-zero coefficient count) of the
+    pass, computed inside the kernel (b200dct_roundtrip_metrics)."""
+    import torch
+
+    ip, idt, ipitch, H, W = _plane(img)
+    if out is None:
+        out = torch.empty_like(img)
+    op, odt, opitch, _, _ = _plane(out)
+    cp, cdt, cpitch = (None, F32, 0) if coef is None else _plane(coef)[:3]
+    nbytes = int(lib().b200dct_metrics_workspace_bytes(H, W))
+    ws = torch.empty(max(1, nbytes // 8), dtype=torch.float64, device=img.device)
+    acc = torch.zeros(3, dtype=torch.float64, device=img.device)
+    with torch.cuda.device(img.device):
+        _check(lib().b200dct_roundtrip_metrics(_plan(plan)._h, ip, idt, ipitch, op, odt, opitch, cp, cdt, cpitch, H, W,
+                                               acc.data_ptr(), ws.data_ptr(), nbytes, _stream(stream)))
+    sse, energy, nnz = acc.tolist()
+    n = H * W
+    return out, (sse / n, 100.0 * (sse / energy) ** 0.5 if energy > 0 else 0.0, int(nnz))
 
 
 def roundtrip_host(h_in, h_out=None, plan: Plan | None = None):

@@ -15,14 +15,58 @@
 #include "dct_kernels.cuh"
 
 namespace b200dct {
-// one launcher per translation unit of kernel instantiations (inst_*.cu)
-cudaError_t launch_direct_sparse(int mode, int qmode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);
-cudaError_t launch_direct_dense(int mode, int qmode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);
-cudaError_t launch_tma_sparse(int mode, int qmode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s);
-cudaError_t launch_tma_dense(int mode, int qmode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s);
+// one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
+#define B200_DECL(tag)                                                                                                  \
+    cudaError_t launch_direct_##tag(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);     \
+    cudaError_t launch_direct_metrics_##tag(int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);      \
+    cudaError_t launch_tma_##tag(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s);
+B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2)
+#undef B200_DECL
+
+static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
+{
+    if (sparse) return q == 0 ? launch_direct_s0(mode, pix, P, g, b, s) : q == 1 ? launch_direct_s1(mode, pix, P, g, b, s) : launch_direct_s2(mode, pix, P, g, b, s);
+    return q == 1 ? launch_direct_d1(mode, pix, P, g, b, s) : launch_direct_d2(mode, pix, P, g, b, s);
+}
+static cudaError_t launch_direct_metrics(bool sparse, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
+{
+    if (sparse) return q == 0 ? launch_direct_metrics_s0(pix, P, g, b, s) : q == 1 ? launch_direct_metrics_s1(pix, P, g, b, s) : launch_direct_metrics_s2(pix, P, g, b, s);
+    return q == 1 ? launch_direct_metrics_d1(pix, P, g, b, s) : launch_direct_metrics_d2(pix, P, g, b, s);
+}
+static cudaError_t launch_tma(bool sparse, int mode, int q, int pix, const TmaParams &P, int g, int b, size_t smem, cudaStream_t s)
+{
+    if (sparse) return q == 0 ? launch_tma_s0(mode, pix, P, g, b, smem, s) : q == 1 ? launch_tma_s1(mode, pix, P, g, b, smem, s) : launch_tma_s2(mode, pix, P, g, b, smem, s);
+    return q == 1 ? launch_tma_d1(mode, pix, P, g, b, smem, s) : launch_tma_d2(mode, pix, P, g, b, smem, s);
+}
 } // namespace b200dct
 
 using namespace b200dct;
+
+// Sums n CTA partial triples in a fixed order and ADDS the totals into acc[0..2].
+static __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, size_t n, double *acc)
+{
+    __shared__ double red[3][256];
+    double v[3] = {0.0, 0.0, 0.0};
+    for (size_t i = threadIdx.x; i < n; i += 256) {
+        v[0] += partials[i * 3];
+        v[1] += partials[i * 3 + 1];
+        v[2] += partials[i * 3 + 2];
+    }
+    for (int q = 0; q < 3; q++) red[q][threadIdx.x] = v[q];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+            for (int q = 0; q < 3; q++) red[q][threadIdx.x] += red[q][threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) acc[threadIdx.x] += red[threadIdx.x][0];
+}
+
+static cudaError_t reduce_partials_sparse(const double *partials, size_t n, double *acc, cudaStream_t s)
+{
+    k_reduce_partials<<<1, 256, 0, s>>>(partials, n, acc);
+    return cudaGetLastError();
+}
 
 struct b200dct_plan {
     float T[64];
@@ -279,7 +323,7 @@ static int tma_max_run = 2;                       // env B200DCT_TMA_RUN: longes
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
 
 static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,
-               cudaStream_t stream)
+               cudaStream_t stream, double *partials = nullptr, double *acc = nullptr)
 {
     tl_launches = 0;
     if (!pl) return B200DCT_ERR_ARG;
@@ -305,7 +349,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     const size_t bytes_per_px = elem_size(in.dt) + elem_size(out.dt) + (coef.ptr ? elem_size(coef.dt) : 0);
     // Dense T (32 FMA/px instead of 22) is FP32-pipe bound as well: direct 98 us vs TMA 105 us.
     const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse);
-    bool use_tma = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && get_encode() != nullptr &&
+    bool use_tma = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && !partials && get_encode() != nullptr &&
                    tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
                    (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
     if (pl->path == B200DCT_PATH_TMA && !use_tma) return B200DCT_ERR_ALIGN;
@@ -348,8 +392,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.run = (uint32_t)tma_max_run;
         const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
-        cudaError_t e = pl->sparse ? launch_tma_sparse(mode, qm, pix, P, grid, nw * 32, smem, stream)
-                                   : launch_tma_dense(mode, qm, pix, P, grid, nw * 32, smem, stream);
+        cudaError_t e = launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream);
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
         tl_path = "tma";
@@ -368,8 +411,20 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     dim3 block(32, 4);
     dim3 grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32));
     if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
-    cudaError_t e = pl->sparse ? launch_direct_sparse(mode, qm, pix, P, grid, block, stream)
-                               : launch_direct_dense(mode, qm, pix, P, grid, block, stream);
+    cudaError_t e;
+    if (partials) {
+        // fused metrics: per-CTA partials, then one fixed-order reduction into acc[0..2]
+        if (mode != MODE_RT || in.ptr == out.ptr) return B200DCT_ERR_ARG;
+        P.partials = partials;
+        e = launch_direct_metrics(pl->sparse, qm, pix, P, grid, block, stream);
+        if (e != cudaSuccess) return (int)e;
+        e = reduce_partials_sparse(partials, (size_t)grid.x * grid.y, acc, stream);
+        if (e != cudaSuccess) return (int)e;
+        tl_launches = 2;
+        tl_path = "direct";
+        return B200DCT_OK;
+    }
+    e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream);
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "direct";
@@ -397,6 +452,25 @@ extern "C" int b200dct_roundtrip(const b200dct_plan *plan, const void *img, b200
 {
     return run(plan, MODE_RT, Plane{img, (int)in_dt, in_pitch}, Plane{out, (int)out_dt, out_pitch},
                Plane{coef_or_null, (int)coef_dt, coef_pitch}, nullptr, H, W, (cudaStream_t)stream);
+}
+
+extern "C" size_t b200dct_metrics_workspace_bytes(int H, int W)
+{
+    if (H <= 0 || W <= 0) return 0;
+    const size_t ctas = (size_t)((H / 8 + 3) / 4) * (size_t)((W / 8 + 31) / 32);
+    return ctas * 3 * sizeof(double);
+}
+
+extern "C" int b200dct_roundtrip_metrics(const b200dct_plan *plan, const void *img, b200dct_dtype in_dt, size_t in_pitch,
+                                         void *out, b200dct_dtype out_dt, size_t out_pitch, void *coef_or_null,
+                                         b200dct_dtype coef_dt, size_t coef_pitch, int H, int W, double *d_acc3,
+                                         void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (!d_acc3 || !workspace || workspace_bytes < b200dct_metrics_workspace_bytes(H, W) || ((uintptr_t)workspace & 7))
+        return B200DCT_ERR_ARG;
+    return run(plan, MODE_RT, Plane{img, (int)in_dt, in_pitch}, Plane{out, (int)out_dt, out_pitch},
+               Plane{coef_or_null, (int)coef_dt, coef_pitch}, nullptr, H, W, (cudaStream_t)stream, (double *)workspace,
+               d_acc3);
 }
 
 // Average device time of `iters` back-to-back identical calls, measured with CUDA events on

@@ -75,6 +75,7 @@ struct DirectParams {
     size_t in_pitch, out_pitch, coef_pitch, shifted_pitch; // bytes
     int bx, by;       // blocks per row / block rows
     int coef_dt;      // DT_F32 / DT_I16
+    double *partials; // METRICS kernels: 3 doubles per CTA {sum (x-y)^2, sum x^2, non-zero coefficients}
     CommonParams cp;
 };
 
@@ -120,15 +121,28 @@ __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
     sfor<4>([&](auto j) { r[IC(j)] = fadd2(r[IC(j)], bc(s)); });
 }
 
-template <int MODE, bool SPARSE, int QMODE, int PIX>
+// METRICS (round trip only): the kernel also accumulates, per CTA, the squared error and the
+// signal energy between the pixels it read and the pixels it wrote (as stored: u8 after
+// clamp+truncate) and the number of non-zero quantised coefficients, and writes them to
+// P.partials[cta]; k_reduce_partials then adds them up in a fixed order (deterministic).
+// The input row is re-read at the end (an L2 hit) instead of being kept in 64 registers.
+template <int MODE, bool SPARSE, int QMODE, int PIX, bool METRICS = false>
 __global__ void __launch_bounds__(128) k_direct(const __grid_constant__ DirectParams P)
 {
     // CTA = 32 block-columns x 4 block-rows; grid.x walks block-rows (no 65535 limit),
     // grid.y walks groups of 32 block-columns.  Lanes of a warp are horizontally adjacent
     // blocks, so each row access of a warp covers one contiguous 1 KiB segment.
-    const int bxi = blockIdx.y * 32 + threadIdx.x;
-    const long long by = (long long)blockIdx.x * 4 + threadIdx.y;
-    if (bxi >= P.bx || by >= P.by) return;
+    static_assert(!METRICS || MODE == MODE_RT, "metrics are defined for the round trip");
+    int bxi = blockIdx.y * 32 + threadIdx.x;
+    long long by = (long long)blockIdx.x * 4 + threadIdx.y;
+    const bool valid = bxi < P.bx && by < P.by;
+    if constexpr (!METRICS) {
+        if (!valid) return;
+    } else if (!valid) { // stay for the CTA reduction; work on block (0,0), store nothing
+        bxi = 0;
+        by = 0;
+    }
+    float m_sse = 0.0f, m_en = 0.0f, m_nnz = 0.0f;
 
     float2 p[8][4];
     // ---- load
@@ -170,7 +184,14 @@ __global__ void __launch_bounds__(128) k_direct(const __grid_constant__ DirectPa
     };
 
     run_block<MODE, SPARSE, QMODE>(p, P.cp, [&](float2 (&c)[8][4]) {
-        if (P.coef) store_coef(P.coef, P.coef_pitch, c);
+        if (P.coef && valid) store_coef(P.coef, P.coef_pitch, c);
+        if constexpr (METRICS) {
+            sfor<8>([&](auto r) {
+                sfor<4>([&](auto j) {
+                    m_nnz += (c[IC(r)][IC(j)].x != 0.0f ? 1.0f : 0.0f) + (c[IC(r)][IC(j)].y != 0.0f ? 1.0f : 0.0f);
+                });
+            });
+        }
     });
 
     // ---- store
@@ -178,13 +199,52 @@ __global__ void __launch_bounds__(128) k_direct(const __grid_constant__ DirectPa
         store_coef(P.out, P.out_pitch, p);
     } else if constexpr (PIX == DT_F32) {
         char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 32;
+        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
         sfor<8>([&](auto r) {
             shift_row(p[IC(r)], 128.0f); // add_matrix_scalar, utils_kernels.cu:29
-            st_row_f32(dst + IC(r) * P.out_pitch, p[IC(r)]);
+            if (valid) st_row_f32(dst + IC(r) * P.out_pitch, p[IC(r)]);
+            if constexpr (METRICS) {
+                float2 x[4];
+                ld_row_f32(src + IC(r) * P.in_pitch, x);
+                sfor<4>([&](auto j) {
+                    const float dx = x[IC(j)].x - p[IC(r)][IC(j)].x, dy = x[IC(j)].y - p[IC(r)][IC(j)].y;
+                    m_sse = __fmaf_rn(dx, dx, m_sse); m_sse = __fmaf_rn(dy, dy, m_sse);
+                    m_en = __fmaf_rn(x[IC(j)].x, x[IC(j)].x, m_en); m_en = __fmaf_rn(x[IC(j)].y, x[IC(j)].y, m_en);
+                });
+            }
         });
     } else {
         char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 8;
-        sfor<8>([&](auto r) { *reinterpret_cast<uint2 *>(dst + IC(r) * P.out_pitch) = pack_u8_plus128(p[IC(r)]); });
+        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
+        sfor<8>([&](auto r) {
+            const uint2 w = pack_u8_plus128(p[IC(r)]);
+            if (valid) *reinterpret_cast<uint2 *>(dst + IC(r) * P.out_pitch) = w;
+            if constexpr (METRICS) { // integers: every partial sum below is exact in float
+                const uint2 xin = __ldg(reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch));
+                sfor<8>([&](auto b) {
+                    const float x = u8_to_float(IC(b) < 4 ? xin.x : xin.y, IC(b) & 3);
+                    const float y = u8_to_float(IC(b) < 4 ? w.x : w.y, IC(b) & 3);
+                    const float d = x - y;
+                    m_sse = __fmaf_rn(d, d, m_sse);
+                    m_en = __fmaf_rn(x, x, m_en);
+                });
+            }
+        });
+    }
+
+    if constexpr (METRICS) {
+        double v[3] = {valid ? (double)m_sse : 0.0, valid ? (double)m_en : 0.0, valid ? (double)m_nnz : 0.0};
+        __shared__ double red[3][4];
+        const int lane = threadIdx.x, w = threadIdx.y;
+        sfor<3>([&](auto q) {
+            for (int o = 16; o > 0; o >>= 1) v[IC(q)] += __shfl_xor_sync(0xffffffffu, v[IC(q)], o);
+            if (lane == 0) red[IC(q)][w] = v[IC(q)];
+        });
+        __syncthreads();
+        if (w == 0 && lane < 3) {
+            const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            P.partials[cta * 3 + lane] = (red[lane][0] + red[lane][1]) + (red[lane][2] + red[lane][3]);
+        }
     }
 }
 

@@ -1,33 +1,50 @@
-// inst_direct.cuh -- instantiates k_direct for one T family (INST_SPARSE = true/false).
+// inst_direct.cuh -- instantiates k_direct for one (T family, quantiser) pair:
+//   INST_SPARSE = 1/0, INST_Q = Q_IMM / Q_PARAM / Q_PARAM_DIV, INST_TAG = name suffix.
+// One small translation unit per pair keeps the parallel build short.
 #include "dct_kernels.cuh"
 
 namespace b200dct {
 
-#define B200_DIRECT_CASE(M, Q, X)                                                   \
-    if (mode == (M) && qmode == (Q) && pix == (X)) {                                \
-        k_direct<M, INST_SPARSE, Q, X><<<grid, block, 0, s>>>(P);                   \
+#define B200_CAT_(a, b) a##b
+#define B200_CAT(a, b) B200_CAT_(a, b)
+
+#define B200_DIRECT_CASE(M, X)                                                      \
+    if (mode == (M) && pix == (X)) {                                                \
+        k_direct<M, INST_SPARSE, INST_Q, X><<<grid, block, 0, s>>>(P);              \
         return cudaGetLastError();                                                  \
     }
-#define B200_DIRECT_MODES(Q, X) \
-    B200_DIRECT_CASE(MODE_FWD, Q, X) B200_DIRECT_CASE(MODE_INV, Q, X) B200_DIRECT_CASE(MODE_RT, Q, X)
 
-cudaError_t INST_NAME(int mode, int qmode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
+cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
 {
-#ifdef B200DCT_FAST_BUILD /* experiment builds: headline kernels only */
-#if INST_SPARSE
-    B200_DIRECT_MODES(Q_IMM, DT_F32)
-    B200_DIRECT_CASE(MODE_RT, Q_IMM, DT_U8)
+    B200_DIRECT_CASE(MODE_RT, DT_F32)
+    B200_DIRECT_CASE(MODE_RT, DT_U8)
+#ifdef B200DCT_FAST_BUILD /* experiment builds: round trip only (+ f32 split for the default quantiser) */
+#if INST_Q == 0
+    B200_DIRECT_CASE(MODE_FWD, DT_F32)
+    B200_DIRECT_CASE(MODE_INV, DT_F32)
 #endif
     return cudaErrorInvalidValue;
+#else
+    B200_DIRECT_CASE(MODE_FWD, DT_F32)
+    B200_DIRECT_CASE(MODE_FWD, DT_U8)
+    B200_DIRECT_CASE(MODE_INV, DT_F32)
+    B200_DIRECT_CASE(MODE_INV, DT_U8)
+    return cudaErrorInvalidValue;
 #endif
-#if INST_SPARSE
-    B200_DIRECT_MODES(Q_IMM, DT_F32)
-    B200_DIRECT_MODES(Q_IMM, DT_U8)
+}
+
+cudaError_t B200_CAT(launch_direct_metrics_, INST_TAG)(int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
+{
+#ifndef B200DCT_FAST_BUILD
+    if (pix == DT_F32) {
+        k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_F32, true><<<grid, block, 0, s>>>(P);
+        return cudaGetLastError();
+    }
+    if (pix == DT_U8) {
+        k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_U8, true><<<grid, block, 0, s>>>(P);
+        return cudaGetLastError();
+    }
 #endif
-    B200_DIRECT_MODES(Q_PARAM, DT_F32)
-    B200_DIRECT_MODES(Q_PARAM, DT_U8)
-    B200_DIRECT_MODES(Q_PARAM_DIV, DT_F32)
-    B200_DIRECT_MODES(Q_PARAM_DIV, DT_U8)
     return cudaErrorInvalidValue;
 }
 

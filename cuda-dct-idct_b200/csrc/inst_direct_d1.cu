@@ -1,0 +1,4 @@
+#define INST_SPARSE 0
+#define INST_Q 1
+#define INST_TAG d1
+#include "inst_direct.cuh"

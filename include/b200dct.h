@@ -130,6 +130,23 @@ int b200dct_roundtrip(const b200dct_plan *plan,
                       void *coef_or_null, b200dct_dtype coef_dt, size_t coef_pitch,
                       int H, int W, void *stream);
 
+/* Fused round trip + quality metrics in the same pass: besides the
+ * pixels (and optional coefficients) the kernel accumulates, between the pixels it read and
+ * the pixels it wrote (as stored: u8 after clamp+truncate, f32 unclamped),
+ *   d_acc3[0] += sum (x - y)^2     d_acc3[1] += sum x^2     d_acc3[2] += non-zero quantised coefficients
+ * so MSE = acc[0]/(H*W), PEEN% = 100*sqrt(acc[0]/acc[1]) (the definitions recovered from
+ * README.md:67-68 of the reference) and the coefficient density need no second pass over the
+ * images.  Per-CTA partial sums go to `workspace` (device, >= b200dct_metrics_workspace_bytes,
+ * caller-owned, 8-byte aligned) and are reduced in a fixed order: results are deterministic,
+ * exact for u8 images.  `out` must not alias `img`.  Runs on the direct kernel family. */
+size_t b200dct_metrics_workspace_bytes(int H, int W);
+int b200dct_roundtrip_metrics(const b200dct_plan *plan,
+                              const void *img, b200dct_dtype in_dt, size_t in_pitch,
+                              void *out, b200dct_dtype out_dt, size_t out_pitch,
+                              void *coef_or_null, b200dct_dtype coef_dt, size_t coef_pitch,
+                              int H, int W, double *d_acc3,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
 /* Host-buffer round trip: what the reference's main() does around its two calls
  * (cudaMalloc, H2D, dct, idct, D2H: main_newAppr.cu:88-124), as one call on the current
  * device.  h_in/h_out are HOST pointers (pinned or pageable), tightly packed rows.

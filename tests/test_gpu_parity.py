@@ -217,6 +217,33 @@ def test_host_roundtrip_and_metrics(dct, oracle):
     assert mse == pytest.approx(wm, rel=1e-9) and peen == pytest.approx(wp, rel=1e-9)
 
 
+@pytest.mark.parametrize("shape", [(8, 8), (256, 256), (72, 1040), (1024, 2048)])
+def test_fused_metrics(dct, oracle, shape):
+    """b200dct_roundtrip_metrics: pixels identical to the plain round trip; MSE/PEEN equal the
+    oracle's double-precision values (u8: exactly, the in-kernel sums are integers;
+    f32: to 1e-6 relative, the in-kernel partials are float) -- spec tolerance is 1e-3;
+    non-zero count equals the coefficient plane's."""
+    img8 = oracle.rand_image_u8(*shape, 7)
+    want8, wcoef = oracle.roundtrip(img8, want_coef=True)
+    out8, (mse, peen, nnz) = dct.roundtrip_with_metrics(dev(img8))
+    assert np.array_equal(host(out8), want8)
+    wm, wp = oracle.metrics(img8, want8)
+    assert mse == pytest.approx(wm, rel=1e-13) and peen == pytest.approx(wp, rel=1e-13)
+    assert nnz == int(np.count_nonzero(wcoef))
+    img = inputs.float_noise(*shape, seed=3)
+    want, wcoef = oracle.roundtrip(img, want_coef=True)
+    coef = torch.empty(shape, dtype=torch.int16, device="cuda")
+    out, (mse, peen, nnz) = dct.roundtrip_with_metrics(dev(img), coef=coef, plan=dct.Plan(keep=oracle.zigzag_mask(10)))
+    want, wcoef = oracle.roundtrip(img, keep=oracle.zigzag_mask(10), want_coef=True)
+    assert np.array_equal(bits(host(out)), bits(want)) and np.array_equal(host(coef), wcoef.astype(np.int16))
+    wm, wp = oracle.metrics(img, want)
+    assert mse == pytest.approx(wm, rel=1e-6) and peen == pytest.approx(wp, rel=1e-6)
+    assert nnz == int(np.count_nonzero(wcoef))
+    with pytest.raises(dct.B200DCTError):
+        x = dev(img)
+        dct.roundtrip_with_metrics(x, out=x)      # aliasing would corrupt the comparison
+
+
 def test_reference_named_entry_points(dct, oracle):
     """dct_all_blocks_cuda / idct_all_blocks_cuda with the reference's calling convention:
     (image, H, W, T_device, result), input left holding image-128."""
