@@ -295,3 +295,25 @@ def test_full_size_properties(dct, oracle):
     assert torch.equal(out8, out.clamp(0, 255).to(torch.uint8))
     mse, peen = dct.metrics(img8, out8)
     assert 330 < mse < 360 and 12 < peen < 13     # Appendix B: 344.38 / 12.593 on rand()%256 data
+
+
+def test_two_gigapixel_image_indexing(dct, oracle):
+    """Maximum sizes: 65536 x 32768 u8 = 2^31 pixels (the reference's `int` indexing caps
+    W*H below 2^31, utils_kernels.cu:12).  Bands at both ends and across the 2^31-byte
+    boundary must match the oracle on both kernel families; f32 46344-row strip likewise."""
+    H, W = 65536, 32768
+    g = torch.Generator(device="cuda").manual_seed(5)
+    img = torch.randint(0, 256, (H, W), device="cuda", generator=g, dtype=torch.uint8)
+    for path in (1, 2):
+        out = dct.roundtrip(img, plan=dct.Plan(path=path))
+        for r0 in (0, H // 2 - 8, H - 16):
+            band = host(img[r0:r0 + 16])
+            assert np.array_equal(host(out[r0:r0 + 16]), oracle.roundtrip(band)), (path, r0)
+        del out
+    del img
+    torch.cuda.empty_cache()
+    H, W = 32768 + 8, 32768     # f32: 4 GiB + a block-row, byte offsets beyond 2^32
+    imgf = torch.randint(0, 256, (H, W), device="cuda", generator=g, dtype=torch.int32).float()
+    out = dct.roundtrip(imgf)
+    for r0 in (0, 32768 - 8, H - 8):
+        assert np.array_equal(bits(host(out[r0:r0 + 8])), bits(oracle.roundtrip(host(imgf[r0:r0 + 8])))), r0

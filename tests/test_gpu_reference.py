@@ -133,3 +133,24 @@ def test_committed_reference_fixtures_match_live_reference(oracle):
         g = np.load(f)
         coef, _ = refgpu.dct("newappr", dev(g["img"].astype(np.float32)), T)
         assert np.array_equal(bits(host(coef)), bits(g["coef"]))
+
+
+def test_cpp_caller_links_against_compat_library(oracle):
+    """tests/cpp/dropin_main.cu is written like the reference's programs (forward-declared
+    dct_all_blocks_cuda / idct_all_blocks_cuda, (height, width) order, device buffers) and is
+    linked against libb200dct_compat.so: it must print the oracle's (= the reference's) numbers."""
+    import re
+    import subprocess
+
+    exe = os.path.join(os.path.dirname(GOLD.rstrip("/")), "..", "cuda-dct-idct_b200", "dropin_demo")
+    exe = os.path.abspath(exe)
+    if not os.path.exists(exe):
+        pytest.skip("dropin_demo not built")
+    for variant in (0, 1):
+        out = subprocess.run([exe, "256", str(variant)], capture_output=True, text=True, timeout=120).stdout
+        m = re.search(r"COEF sum=(-?\d+) sumabs=(\d+) nonzero=(\d+)", out)
+        assert m, out
+        assert tuple(map(int, m.groups())) == (-306, 114414, 46317)         # SURVEY.md Appendix B, N=256
+        assert int(re.search(r"PIX sumu8=(\d+)", out).group(1)) == 8329775
+        assert "DCT (256,256):" in out and "IDCT (256,256):" in out          # the reference's timing lines
+        assert "INPUT_AFTER first=-58 (was 70)" in out                       # input left as image-128
