@@ -90,6 +90,24 @@ def test_roundtrip_u8(dct, oracle, path, shape):
     assert np.array_equal(bits(host(c)), bits(want_coef))
 
 
+def test_auto_path_policy(dct, oracle):
+    """AUTO: the TMA family for large HBM-bound sparse-T calls, the direct family otherwise."""
+    small = torch.zeros(256, 256, device="cuda")
+    big = torch.zeros(4096, 4096, device="cuda")
+    dct.roundtrip(small)
+    assert dct.api.last_path() == "direct"
+    dct.roundtrip(big)
+    assert dct.api.last_path() == "tma"
+    dct.forward(big)
+    assert dct.api.last_path() == "tma"
+    dct.roundtrip(big.to(torch.uint8))
+    assert dct.api.last_path() == "direct"          # 2 B/px: FP32-pipe bound
+    dct.roundtrip(big, plan=dct.Plan(T=oracle.dct2_T()))
+    assert dct.api.last_path() == "direct"          # dense T: FP32-pipe bound
+    dct.roundtrip(big.to(torch.uint8), coef=torch.empty(4096, 4096, device="cuda"))
+    assert dct.api.last_path() == "tma"             # + f32 coefficient plane: 6 B/px
+
+
 @pytest.mark.parametrize("shape", [(8, 8), (8, 16), (72, 1040), (16, 24)])
 def test_auto_path_falls_back_to_direct_on_narrow_or_odd_widths(dct, oracle, shape):
     """W % 32 != 0 cannot be tiled by the f32 TMA view: AUTO silently uses the direct kernels,
