@@ -25,7 +25,7 @@ from .api import (  # noqa: F401
     roundtrip_with_metrics,
     zigzag_mask,
 )
-from . import api, dist  # noqa: F401
+from . import api, dist, imageio  # noqa: F401
 from .build import build  # noqa: F401
 from .stripes import stripe_rows  # noqa: F401
 

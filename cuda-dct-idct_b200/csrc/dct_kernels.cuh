@@ -82,8 +82,10 @@ struct DirectParams {
 // ---- per-row global accessors (one 8-pixel row of one block) ----
 __device__ __forceinline__ void ld_row_f32(const void *base, float2 (&r)[4])
 {
-    const float4 a = __ldg(reinterpret_cast<const float4 *>(base));
-    const float4 b = __ldg(reinterpret_cast<const float4 *>(base) + 1);
+    // plain (coherent) loads: the forward kernel may write image-128 back over the very
+    // rows it read (the reference's in-place sub_matrix_scalar), which rules out ld.global.nc
+    const float4 a = reinterpret_cast<const float4 *>(base)[0];
+    const float4 b = reinterpret_cast<const float4 *>(base)[1];
     r[0] = make_float2(a.x, a.y); r[1] = make_float2(a.z, a.w);
     r[2] = make_float2(b.x, b.y); r[3] = make_float2(b.z, b.w);
 }
@@ -430,15 +432,20 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     const uint32_t stride = gridDim.x * nwarps;
     uint32_t *const sched = P.sched;
     uint32_t run_left = 0; // lane 0: tiles still owned after the current one
-    auto claim_next = [&](uint32_t cur) -> uint32_t { // lane 0 only; returns the next tile (>= ntiles: none)
-        if (!sched) return cur + stride;
-        if (run_left) { run_left--; return cur + 1; }
-        const uint32_t t = atomicAdd(&sched[0], 1u);
+    auto ticket_tile = [&](uint32_t t) -> uint32_t { // lane 0 only; first tile of ticket t (>= ntiles: none)
         if (t < P.run_tickets) { run_left = P.run - 1; return t * P.run; }
+        run_left = 0;
         return P.run_tickets * P.run + (t - P.run_tickets); // may be >= ntiles: the losing ticket
     };
+    auto claim_next = [&](uint32_t cur) -> uint32_t { // lane 0 only; returns the next tile
+        if (!sched) return cur + stride;
+        if (run_left) { run_left--; return cur + 1; }
+        return ticket_tile(atomicAdd(&sched[0], 1u) + stride);
+    };
+    // the first `stride` tickets are pre-assigned (warp-major, CTA-minor) so that no atomic
+    // round trip sits in front of the first TMA load; the counter hands out the rest
     uint32_t tile = 0;
-    if (lane == 0) tile = sched ? claim_next(0) : warp * gridDim.x + blockIdx.x;
+    if (lane == 0) tile = sched ? ticket_tile(warp * gridDim.x + blockIdx.x) : warp * gridDim.x + blockIdx.x;
     tile = __shfl_sync(0xffffffffu, tile, 0);
     const bool in_is_f32 = (MODE == MODE_INV) ? (P.coef_dt == DT_F32) : (PIX == DT_F32);
     const uint32_t in_bytes = (MODE == MODE_INV) ? (P.coef_dt == DT_F32 ? 8192u : 4096u) : tile_bytes<PIX>();

@@ -335,3 +335,19 @@ def test_two_gigapixel_image_indexing(dct, oracle):
     out = dct.roundtrip(imgf)
     for r0 in (0, 32768 - 8, H - 8):
         assert np.array_equal(bits(host(out[r0:r0 + 8])), bits(oracle.roundtrip(host(imgf[r0:r0 + 8])))), r0
+
+
+def test_file_to_file_flow(dct, oracle, tmp_path):
+    """The reference program's whole flow (main_newAppr.cu:26-165): image file in, transformed
+    image file out.  PGM is lossless, so the file equals the oracle's u8 reconstruction."""
+    img = oracle.rand_image_u8(100, 203, 9)             # ragged: cropped to 96 x 200
+    src, dst = str(tmp_path / "in.pgm"), str(tmp_path / "out.pgm")
+    dct.imageio.save_gray(src, img)
+    mse, peen = dct.imageio.transform_file(src, dst)
+    want = oracle.roundtrip(np.ascontiguousarray(img[:96, :200]))
+    assert np.array_equal(dct.imageio.load_gray(dst), want)
+    wm, wp = oracle.metrics(np.ascontiguousarray(img[:96, :200]), want)
+    assert mse == pytest.approx(wm, rel=1e-12) and peen == pytest.approx(wp, rel=1e-12)
+    jpg = str(tmp_path / "out.jpg")
+    dct.imageio.transform_file(src, jpg)                # quality-100 JPEG, as the reference saves
+    assert dct.imageio.load_gray(jpg).shape == (96, 200)

@@ -133,3 +133,20 @@ def test_stripe_rows(m):
         m.stripe_rows(12, 2, 0)
     with pytest.raises(ValueError):
         m.stripe_rows(16, 2, 2)
+
+
+def test_image_files_roundtrip_on_host(m, tmp_path):
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (37, 53)).astype(np.uint8)
+    p = str(tmp_path / "a.pgm")
+    m.imageio.save_gray(p, img)
+    assert np.array_equal(m.imageio.load_gray(p), img)
+    with open(p, "rb") as f:
+        raw = f.read()
+    with open(p, "wb") as f:                      # header with a comment line
+        f.write(b"P5\n# made by a test\n53 37\n255\n" + raw[raw.index(b"255\n") + 4:])
+    assert np.array_equal(m.imageio.load_gray(p), img)
+    png = str(tmp_path / "a.png")
+    m.imageio.save_gray(png, img)
+    assert np.array_equal(m.imageio.load_gray(png), img)
+    assert m.imageio.crop_to_blocks(img).shape == (32, 48)
