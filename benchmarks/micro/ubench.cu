@@ -21,6 +21,8 @@ template<int MODE> __global__ void k(float* out, float s, unsigned long long* cy
       if (MODE==5) a[i] = __fadd_rz(a[i], t);                           // FADD.RZ
       if (MODE==6) a[i] = __uint_as_float(__float_as_uint(a[i]) & 0x80000000u | 0x3f000000u) + a[(i+1)&7]; // LOP3+FADD
       if (MODE==7) a[i] = __fdiv_rn(a[i], t);                           // true division
+      if (MODE==8) { unsigned r; asm volatile("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(a[i])); a[i] = __uint_as_float(r | 0x3f800000u); } // F2IP + LOP3
+      if (MODE==9) a[i] = fminf(fmaxf(a[i], 0.f), t);                   // 2x FMNMX
     }
   }
   long long t1 = clock64();
@@ -41,7 +43,7 @@ template<int MODE> void run(const char* name, int warps){
 int main(){
   for (int w : {4, 8, 16, 32}) {
     run<0>("FFMA reg", w); run<1>("FFMA imm", w); run<2>("FFMA2 reg", w); run<3>("FFMA2 imm", w);
-    run<4>("FRND", w); run<5>("FADD.RZ", w); run<6>("LOP3+FADD", w); run<7>("fdiv_rn", w);
+    run<4>("FRND", w); run<5>("FADD.RZ", w); run<6>("LOP3+FADD", w); run<7>("fdiv_rn", w); run<8>("F2IP.U8+LOP3", w); run<9>("FMNMX x2", w);
   }
   return 0;
 }

@@ -316,17 +316,19 @@ __device__ __forceinline__ float u8_to_float(uint32_t word, int byte)
     const uint32_t bits = __byte_perm(word, 0x4B000000u, 0x7440u | (uint32_t)byte);
     return __uint_as_float(bits) - 8388608.0f;
 }
-// float pixel -> u8 as convertToUnsignedChar (utils.cu:21): clamp to [0,255], truncate.
-// Returns 2^23 + trunc(v) as float bits; the low byte is the pixel.
-__device__ __forceinline__ uint32_t pixel_u8_bits(float v)
+// float pixel -> u8 as convertToUnsignedChar (utils.cu:21): clamp to [0,255], then truncate.
+// cvt.rzi.sat.u8.f32 does both in one instruction (SASS F2IP.U8.F32.TRUNC): saturation to
+// [0,255] commutes with truncation toward zero, NaN gives 0 like fmaxf(NaN, 0).
+__device__ __forceinline__ uint32_t pixel_u8(float v)
 {
-    v = fminf(fmaxf(v, 0.0f), 255.0f);
-    return __float_as_uint(__fadd_rz(v, 8388608.0f));
+    uint32_t r;
+    asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
 }
 __device__ __forceinline__ uint32_t pack4_u8(float a, float b, float c, float d)
 {
-    const uint32_t lo = __byte_perm(pixel_u8_bits(a), pixel_u8_bits(b), 0x0040);
-    const uint32_t hi = __byte_perm(pixel_u8_bits(c), pixel_u8_bits(d), 0x0040);
+    const uint32_t lo = __byte_perm(pixel_u8(a), pixel_u8(b), 0x0040);
+    const uint32_t hi = __byte_perm(pixel_u8(c), pixel_u8(d), 0x0040);
     return __byte_perm(lo, hi, 0x5410);
 }
 // integer-valued float coefficient -> saturating int16

@@ -29,6 +29,13 @@ KEYS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "memory_l1_wavefronts_shared_ideal",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio",
+    "smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio", "smsp__average_warp_latency_issue_stalled_wait.ratio",
+    "smsp__average_warp_latency_issue_stalled_not_selected.ratio", "smsp__average_warp_latency_issue_stalled_dispatch_stall.ratio",
+    "smsp__average_warp_latency_issue_stalled_barrier.ratio", "smsp__average_warp_latency_issue_stalled_membar.ratio",
+    "smsp__average_warp_latency_issue_stalled_lg_throttle.ratio", "smsp__average_warp_latency_issue_stalled_mio_throttle.ratio",
+    "smsp__average_warp_latency_issue_stalled_no_instruction.ratio", "smsp__average_warp_latency_issue_stalled_branch_resolving.ratio",
+    "smsp__average_warp_latency_issue_stalled_sleeping.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
 ]
 
 
@@ -39,8 +46,10 @@ def raw(rep):
 
 
 def main():
-    rnd, rep = sys.argv[1], sys.argv[2]
-    launches = sys.argv[3] if len(sys.argv) > 3 else None
+    args = [a for a in sys.argv[1:] if a != "--no-traffic"]
+    write_traffic = "--no-traffic" not in sys.argv     # only the headline kernel feeds bench.py's roofline.traffic
+    rnd, rep = args[0], args[1]
+    launches = args[2] if len(args) > 2 else None
     os.makedirs("profiles", exist_ok=True)
     hdr, units, data = raw(rep)
     kname = data[0][hdr.index("Kernel Name")]
@@ -62,9 +71,10 @@ def main():
                "note": "one ncu --set full capture, 8192x8192 f32; writes still dirty in the 126 MB L2 when the kernel "
                        "ends are not counted by dram__bytes_write, hence write < 268.4 MB",
                "report": os.path.basename(rep)}
-    with open(f"profiles/{rnd}_traffic.json", "w") as f:
-        json.dump(traffic, f, indent=1)
-    print("wrote", f"profiles/{rnd}_ncu_{short}.txt", f"profiles/{rnd}_traffic.json")
+    if write_traffic:
+        with open(f"profiles/{rnd}_traffic.json", "w") as f:
+            json.dump(traffic, f, indent=1)
+    print("wrote", f"profiles/{rnd}_ncu_{short}.txt", f"profiles/{rnd}_traffic.json" if write_traffic else "")
     if launches:
         rows = [r for r in csv.reader(open(launches)) if len(r) > 10]
         h = rows[0]
