@@ -52,7 +52,9 @@ def main():
     ap.add_argument("--dtype", default="u8", choices=["u8", "f32"])
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--gather", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="time the optional NCCL all-gather of the stripes")
+    ap.add_argument("--fused-gather", action="store_true",
+                    help="transform straight into rank 0's image over NVLink peer stores (dist.PeerImage)")
     args = ap.parse_args()
 
     rank, local_rank, world = m.dist.init()
@@ -102,13 +104,43 @@ def main():
         torch.cuda.synchronize()
         gather_ms = m.dist.max_over_ranks(e0.elapsed_time(e1), dev)
         del full
+    fused_ms, fused_ok = None, None
+    if args.fused_gather and world > 1:
+        peer = m.dist.PeerImage(H, W, img.dtype, dev)
+        dst = peer.stripe_on(0, r0, r1)               # rows [r0, r1) of rank 0's full image
+        for _ in range(3):
+            m.roundtrip(img, out=dst, plan=plan)
+            peer.barrier()
+        torch.cuda.synchronize()
+        m.dist.barrier()
+        e0.record()
+        for _ in range(args.steps):
+            m.roundtrip(img, out=dst, plan=plan)
+            peer.barrier()
+        e1.record()
+        torch.cuda.synchronize()
+        m.dist.barrier()
+        fused_ms = m.dist.max_over_ranks(e0.elapsed_time(e1) / args.steps, dev)
+        if rank == 0:      # the assembled image: bands across every stripe boundary vs the oracle
+            full = peer.local()
+            fused_ok = True
+            for r in range(world):
+                a0, a1 = m.stripe_rows(H, world, r)
+                for b0 in (a0, a1 - 16):
+                    band = inputs.splitmix_u8(16 * W, 42, b0 * W).reshape(16, W)
+                    ref = o.roundtrip(band if args.dtype == "u8" else band.astype(np.float32))
+                    got = full[b0:b0 + 16].cpu().numpy()
+                    fused_ok = fused_ok and (np.array_equal(got, ref) if args.dtype == "u8"
+                                             else np.array_equal(got.view(np.uint32), ref.view(np.uint32)))
+        m.dist.barrier()
     es = 1 if args.dtype == "u8" else 4
     if rank == 0:
         print(json.dumps({
             "workload": f"{H}x{W} {args.dtype} image striped by block-rows over {world} GPU(s) (= {H * W // (8192 * 8192)} images of 8192^2)",
             "n_gpus": world, "ms_per_step": ms, "gpixel_s": H * W / ms / 1e6, "gb_s_per_gpu": 2 * es * H * W / world / ms / 1e6,
             "rows_per_gpu": r1 - r0, "kernel_path": m.api.last_path(), "parity_vs_oracle_bit_exact": bool(ok_all),
-            "optional_gather_ms": gather_ms, "steps": args.steps, "collective_on_data_path": "none"}))
+            "optional_gather_ms": gather_ms, "fused_transform_plus_gather_ms": fused_ms,
+            "fused_gather_parity_bit_exact": fused_ok, "steps": args.steps, "collective_on_data_path": "none"}))
     m.dist.barrier()
     m.dist.shutdown()
 

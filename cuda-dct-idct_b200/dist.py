@@ -94,3 +94,35 @@ def gather_stripes(stripe, H: int, dst: int = 0):
     if rank != dst:
         return None
     return torch.cat([p[: b - a] for p, (a, b) in zip(parts, spans)], 0)
+
+
+class PeerImage:
+    """A full-size image in symmetric (peer-mapped) memory, for the FUSED transform+gather.
+
+    Every rank allocates the same H x W buffer and exchanges handles once
+    (torch.distributed._symmetric_memory: CUDA VMM allocations mapped into every rank's
+    address space over NVLink/NVSwitch).  `stripe_on(dst, r0, r1)` is then an ordinary CUDA
+    tensor view of rows [r0, r1) of rank `dst`'s buffer: handing it to the kernels as the
+    OUTPUT plane makes each rank's transform write its finished stripe straight into the
+    destination GPU's HBM with plain peer stores -- the gather rides on the transform's own
+    stores, tile by tile, instead of running as a separate NCCL all-gather afterwards.
+    """
+
+    def __init__(self, H: int, W: int, dtype, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.H, self.W, self.dtype = H, W, dtype
+        self.buf = symm_mem.empty((H, W), dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+
+    def stripe_on(self, dst_rank: int, r0: int, r1: int):
+        return self.hdl.get_buffer(dst_rank, (r1 - r0, self.W), self.dtype, r0 * self.W)
+
+    def local(self):
+        return self.buf
+
+    def barrier(self):
+        """Stream-ordered barrier over all ranks (signal pads): after it every peer's stores
+        issued before its own barrier() are visible."""
+        self.hdl.barrier()
