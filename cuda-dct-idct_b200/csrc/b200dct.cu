@@ -353,7 +353,13 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // 3072^2 14.7 vs 18.4, 4096^2 27.5 vs 26.7 (profiles/r01_small_sizes.txt).
     const bool big = (unsigned long long)H * (unsigned long long)W >= (12ull << 20);
     const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big);
-    bool use_tma = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && !partials && get_encode() != nullptr &&
+    // Under stream capture the launch may later be replayed concurrently with anything, so the
+    // ticket counters cannot be used; the hardware-scheduled direct family (86.9 us at 8192^2)
+    // then beats the TMA family's static split (99.8 us), unless TMA was asked for explicitly.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+    bool use_tma = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !(capturing && pl->path == B200DCT_PATH_AUTO) &&
+                   !shifted && !partials && get_encode() != nullptr &&
                    tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
                    (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
     if (pl->path == B200DCT_PATH_TMA && !use_tma) return B200DCT_ERR_ALIGN;
@@ -383,9 +389,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.has_coef = coef.ptr ? 1 : 0;
 
         // a captured launch may be replayed concurrently with anything: static split there
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        if (tma_dynamic && cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
-            P.sched = sched_slot();
+        if (tma_dynamic && !capturing) P.sched = sched_slot();
         P.cp = pl->cp;
         const int nw = tma_warps;
         const size_t smem = (size_t)nw * WARP_SMEM_BYTES + (size_t)nw * 8 + 1024;

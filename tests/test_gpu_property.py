@@ -92,17 +92,28 @@ def test_concurrent_streams_share_nothing(dct, oracle):
         assert np.array_equal(bits(host(y)), bits(oracle.roundtrip(oracle.rand_image(512, 512, i))))
 
 
-def test_cuda_graph_capture_uses_static_schedule(dct, oracle):
-    img = torch.from_numpy(oracle.rand_image(512, 512, 3)).cuda()
+@pytest.mark.parametrize("path,expect", [(0, "direct"), (2, "tma")])
+def test_cuda_graph_capture(dct, oracle, path, expect):
+    """Captured launches never use the ticket counters: AUTO takes the direct family, a forced
+    TMA plan the static tile split; replays stay exact."""
+    N = 4096                                          # large enough for AUTO to pick TMA outside capture
+    img = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float()
     out = torch.empty_like(img)
-    dct.roundtrip(img, out=out)          # warm-up outside capture
+    plan = dct.Plan(path=path)
+    dct.roundtrip(img, out=out, plan=plan)           # warm-up outside capture
+    assert dct.api.last_path() == "tma"
+    want = out.clone()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
     with torch.cuda.graph(g, stream=s):
-        dct.roundtrip(img, out=out, stream=torch.cuda.current_stream())
+        dct.roundtrip(img, out=out, plan=plan, stream=torch.cuda.current_stream())
+        captured_path = dct.api.last_path()
+    assert captured_path == expect
     out.zero_()
     for _ in range(3):
         g.replay()
     torch.cuda.synchronize()
-    assert np.array_equal(bits(host(out)), bits(oracle.roundtrip(oracle.rand_image(512, 512, 3))))
+    assert torch.equal(out.view(torch.int32), want.view(torch.int32))
+    band = host(img[:16])
+    assert np.array_equal(bits(host(out[:16])), bits(oracle.roundtrip(band)))
