@@ -108,6 +108,13 @@ def main():
             if N in (2048, 8192):
                 for k in (6, 7, 8, 9, 10):
                     add(N, f"new/mask k={k} f32", time_ms(lambda i: m.roundtrip(f32[i % nb], out=out[i % nb], plan=plans[f"k{k}"]), iters), 8, 1)
+        if have_ref.get("newappr") is not None and N <= 2048:
+            # config 1 / README "DCT on CPU (Sequential)": the oracle, one thread, same generator
+            try:
+                cpu_img = o.rand_image(N, N, 42)
+                add(N, "cpu/oracle 1 thread", o.time_roundtrip(cpu_img, reps=3, threads=1) * 1e3, 8, 0, "sequential C restatement, srand(42) image")
+            except Exception as e:  # pragma: no cover
+                print("cpu baseline skipped:", e)
         add(N, "new/dense(DCT-II) f32", time_ms(lambda i: m.roundtrip(f32[i % nb], out=out[i % nb], plan=plans["dense"]), iters), 8, 1, m.api.last_path())
         # ---- reference kernels, their own event timers
         if have_ref.get("newappr") and N <= 8192:

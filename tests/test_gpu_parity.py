@@ -351,3 +351,21 @@ def test_file_to_file_flow(dct, oracle, tmp_path):
     jpg = str(tmp_path / "out.jpg")
     dct.imageio.transform_file(src, jpg)                # quality-100 JPEG, as the reference saves
     assert dct.imageio.load_gray(jpg).shape == (96, 200)
+
+
+@pytest.mark.parametrize("path", ["tma", "direct"])
+def test_in_place_calls(dct, oracle, path):
+    """out may alias in: every block (tile) is read completely before it is written."""
+    img = oracle.rand_image(128, 256, 17)
+    plan = dct.Plan(path=PATHS[path])
+    d = dev(img)
+    dct.roundtrip(d, out=d, plan=plan)
+    assert np.array_equal(bits(host(d)), bits(oracle.roundtrip(img)))
+    d = dev(img)
+    dct.forward(d, coef=d, plan=plan)
+    assert np.array_equal(bits(host(d)), bits(oracle.dct(img)))
+    dct.inverse(d, img=d, plan=plan)
+    assert np.array_equal(bits(host(d)), bits(oracle.roundtrip(img)))
+    u8 = dev(img.astype(np.uint8))
+    dct.roundtrip(u8, out=u8, plan=plan)
+    assert np.array_equal(host(u8), oracle.roundtrip(img.astype(np.uint8)))
