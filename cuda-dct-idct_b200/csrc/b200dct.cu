@@ -17,26 +17,26 @@
 namespace b200dct {
 // one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
 #define B200_DECL(tag)                                                                                                  \
-    cudaError_t launch_direct_##tag(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);     \
+    cudaError_t launch_direct_##tag(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);     \
     cudaError_t launch_direct_metrics_##tag(int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);      \
-    cudaError_t launch_tma_##tag(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s);
+    cudaError_t launch_tma_##tag(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);
 B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2)
 #undef B200_DECL
 
-static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
+static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
 {
-    if (sparse) return q == 0 ? launch_direct_s0(mode, pix, P, g, b, s) : q == 1 ? launch_direct_s1(mode, pix, P, g, b, s) : launch_direct_s2(mode, pix, P, g, b, s);
-    return q == 1 ? launch_direct_d1(mode, pix, P, g, b, s) : launch_direct_d2(mode, pix, P, g, b, s);
+    if (sparse) return q == 0 ? launch_direct_s0(mode, pix, P, g, b, s, pdl) : q == 1 ? launch_direct_s1(mode, pix, P, g, b, s, pdl) : launch_direct_s2(mode, pix, P, g, b, s, pdl);
+    return q == 1 ? launch_direct_d1(mode, pix, P, g, b, s, pdl) : launch_direct_d2(mode, pix, P, g, b, s, pdl);
 }
 static cudaError_t launch_direct_metrics(bool sparse, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
 {
     if (sparse) return q == 0 ? launch_direct_metrics_s0(pix, P, g, b, s) : q == 1 ? launch_direct_metrics_s1(pix, P, g, b, s) : launch_direct_metrics_s2(pix, P, g, b, s);
     return q == 1 ? launch_direct_metrics_d1(pix, P, g, b, s) : launch_direct_metrics_d2(pix, P, g, b, s);
 }
-static cudaError_t launch_tma(bool sparse, int mode, int q, int pix, const TmaParams &P, int g, int b, size_t smem, cudaStream_t s)
+static cudaError_t launch_tma(bool sparse, int mode, int q, int pix, const TmaParams &P, int g, int b, size_t smem, cudaStream_t s, bool pdl)
 {
-    if (sparse) return q == 0 ? launch_tma_s0(mode, pix, P, g, b, smem, s) : q == 1 ? launch_tma_s1(mode, pix, P, g, b, smem, s) : launch_tma_s2(mode, pix, P, g, b, smem, s);
-    return q == 1 ? launch_tma_d1(mode, pix, P, g, b, smem, s) : launch_tma_d2(mode, pix, P, g, b, smem, s);
+    if (sparse) return q == 0 ? launch_tma_s0(mode, pix, P, g, b, smem, s, pdl) : q == 1 ? launch_tma_s1(mode, pix, P, g, b, smem, s, pdl) : launch_tma_s2(mode, pix, P, g, b, smem, s, pdl);
+    return q == 1 ? launch_tma_d1(mode, pix, P, g, b, smem, s, pdl) : launch_tma_d2(mode, pix, P, g, b, smem, s, pdl);
 }
 } // namespace b200dct
 
@@ -320,6 +320,20 @@ uint32_t *sched_slot()
 static bool tma_dynamic = true; // env B200DCT_TMA_STATIC=1 forces the static tile split
 static int tma_warps = B200DCT_TMA_DEFAULT_WARPS; // warps per CTA of the persistent kernel (env B200DCT_TMA_WARPS, 1..TMA_MAX_WARPS)
 static int tma_max_run = 2;                       // env B200DCT_TMA_RUN: longest run of tiles per claim
+// Programmatic dependent launch (default on; env B200DCT_PDL=0 turns it off): consecutive kernels
+// of this library in one stream overlap the next kernel's CTA launch and set-up with the previous
+// kernel's tail.  Every kernel executes griddepcontrol.wait before its first global-memory access,
+// so stream-order data dependencies (forward -> inverse) stay intact.  8192^2 f32 round trip,
+// back to back: 83.9 -> 81.8 us (profiles/r01_pdl.txt).
+static bool use_pdl()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *p = getenv("B200DCT_PDL");
+        v = (p && atoi(p) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
 
 static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,
@@ -400,7 +414,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.run = (uint32_t)tma_max_run;
         const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
-        cudaError_t e = launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream);
+        cudaError_t e = launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing);
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
         tl_path = "tma";
@@ -432,7 +446,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         tl_path = "direct";
         return B200DCT_OK;
     }
-    e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream);
+    e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream, use_pdl() && !capturing);
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "direct";

@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(128) k_direct(const __grid_constant__ DirectPa
         by = 0;
     }
     float m_sse = 0.0f, m_en = 0.0f, m_nnz = 0.0f;
+    // programmatic dependent launch (no-ops unless the host asked for it): see k_tma
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     float2 p[8][4];
     // ---- load
@@ -457,11 +460,16 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
         else tma_load_2d(in_buf, &P.in_map, bar, tx * 256, ty * 8);
     };
 
+    // Programmatic dependent launch (only when the host asked for it; no-ops otherwise): let
+    // the next kernel in the stream take this SM the moment this CTA leaves it, and do not
+    // touch global memory before every earlier kernel has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (tile < P.ntiles) issue_load(tile);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (lane == 0 && tile < P.ntiles) issue_load(tile);
     __syncwarp();
 
     uint32_t parity = 0;

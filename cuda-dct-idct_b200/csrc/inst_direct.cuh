@@ -10,11 +10,19 @@ namespace b200dct {
 
 #define B200_DIRECT_CASE(M, X)                                                      \
     if (mode == (M) && pix == (X)) {                                                \
-        k_direct<M, INST_SPARSE, INST_Q, X><<<grid, block, 0, s>>>(P);              \
-        return cudaGetLastError();                                                  \
+        cudaLaunchConfig_t cfg = {};                                                \
+        cfg.gridDim = grid;                                                         \
+        cfg.blockDim = block;                                                       \
+        cfg.stream = s;                                                             \
+        cudaLaunchAttribute attr[1];                                                \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;            \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                     \
+        cfg.attrs = attr;                                                           \
+        cfg.numAttrs = pdl ? 1 : 0;                                                 \
+        return cudaLaunchKernelEx(&cfg, k_direct<M, INST_SPARSE, INST_Q, X>, P);    \
     }
 
-cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
+cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
 {
     B200_DIRECT_CASE(MODE_RT, DT_F32)
     B200_DIRECT_CASE(MODE_RT, DT_U8)

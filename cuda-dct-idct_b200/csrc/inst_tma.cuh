@@ -11,11 +11,20 @@ namespace b200dct {
         auto kern = k_tma<M, INST_SPARSE, INST_Q, X>;                                                 \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
-        kern<<<grid, block, smem, s>>>(P);                                                            \
-        return cudaGetLastError();                                                                    \
+        cudaLaunchConfig_t cfg = {};                                                                  \
+        cfg.gridDim = dim3((unsigned)grid);                                                           \
+        cfg.blockDim = dim3((unsigned)block);                                                         \
+        cfg.dynamicSmemBytes = smem;                                                                  \
+        cfg.stream = s;                                                                               \
+        cudaLaunchAttribute attr[1];                                                                  \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                                       \
+        cfg.attrs = attr;                                                                             \
+        cfg.numAttrs = pdl ? 1 : 0;                                                                   \
+        return cudaLaunchKernelEx(&cfg, kern, P);                                                     \
     }
 
-cudaError_t B200_CAT(launch_tma_, INST_TAG)(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s)
+cudaError_t B200_CAT(launch_tma_, INST_TAG)(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl)
 {
     B200_TMA_CASE(MODE_RT, DT_F32)
     B200_TMA_CASE(MODE_RT, DT_U8)
