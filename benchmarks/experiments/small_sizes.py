@@ -3,7 +3,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import cuda_dct_idct_b200 as m
-for N in (64, 128, 256, 512, 1024, 1536, 2048, 3072, 4096):
+import os as _os
+SIZES = [int(x) for x in _os.environ.get("SIZES", "64,128,256,512,1024,1536,2048,3072,4096").split(",")]
+for N in SIZES:
     x = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float(); y = torch.empty_like(x)
     r = []
     for path in (2, 1):

@@ -362,10 +362,11 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // the direct family's 16 resident warps per SM (69.7 vs 84 us at 8192^2, round 1).
     const size_t bytes_per_px = elem_size(in.dt) + elem_size(out.dt) + (coef.ptr ? elem_size(coef.dt) : 0);
     // Dense T (32 FMA/px instead of 22) is FP32-pipe bound as well: direct 98 us vs TMA 105 us.
-    // Below ~12 Mpixel the persistent kernel's fixed costs (descriptor fetch, barrier set-up,
-    // one CTA per SM) lose to the direct family: 256^2 4.1-6.2 us vs 8.2 us, 2048^2 10.3 vs 12.9,
-    // 3072^2 14.7 vs 18.4, 4096^2 27.5 vs 26.7 (profiles/r01_small_sizes.txt).
-    const bool big = (unsigned long long)H * (unsigned long long)W >= (12ull << 20);
+    // Below ~28 Mpixel the persistent kernel's fixed costs (descriptor fetch, barrier set-up,
+    // one CTA per SM) lose to the direct family (C-loop timings with dependent launch,
+    // profiles/r01_small_sizes.txt): 256^2 3.4 vs 6.7 us, 2048^2 7.9 vs 9.7, 4096^2 22.9 vs 24.6,
+    // 5120^2 34.9 vs 35.0, 6144^2 48.9 vs 48.0, 8192^2 83.8 vs 81.8.
+    const bool big = (unsigned long long)H * (unsigned long long)W >= (28ull << 20);
     const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big);
     // Under stream capture the launch may later be replayed concurrently with anything, so the
     // ticket counters cannot be used; the hardware-scheduled direct family (86.9 us at 8192^2)

@@ -93,7 +93,7 @@ def test_roundtrip_u8(dct, oracle, path, shape):
 def test_auto_path_policy(dct, oracle):
     """AUTO: the TMA family for large HBM-bound sparse-T calls, the direct family otherwise."""
     small = torch.zeros(256, 256, device="cuda")
-    big = torch.zeros(4096, 4096, device="cuda")
+    big = torch.zeros(6144, 6144, device="cuda")
     dct.roundtrip(small)
     assert dct.api.last_path() == "direct"
     dct.roundtrip(big)
@@ -104,7 +104,7 @@ def test_auto_path_policy(dct, oracle):
     assert dct.api.last_path() == "direct"          # 2 B/px: FP32-pipe bound
     dct.roundtrip(big, plan=dct.Plan(T=oracle.dct2_T()))
     assert dct.api.last_path() == "direct"          # dense T: FP32-pipe bound
-    dct.roundtrip(big.to(torch.uint8), coef=torch.empty(4096, 4096, device="cuda"))
+    dct.roundtrip(big.to(torch.uint8), coef=torch.empty(6144, 6144, device="cuda"))
     assert dct.api.last_path() == "tma"             # + f32 coefficient plane: 6 B/px
 
 

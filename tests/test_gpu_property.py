@@ -96,7 +96,7 @@ def test_concurrent_streams_share_nothing(dct, oracle):
 def test_cuda_graph_capture(dct, oracle, path, expect):
     """Captured launches never use the ticket counters: AUTO takes the direct family, a forced
     TMA plan the static tile split; replays stay exact."""
-    N = 4096                                          # large enough for AUTO to pick TMA outside capture
+    N = 6144                                          # large enough for AUTO to pick TMA outside capture
     img = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float()
     out = torch.empty_like(img)
     plan = dct.Plan(path=path)
