@@ -335,6 +335,8 @@ def run_ours(args):
                                "fused DCT+quant+dequant+IDCT (BASELINE configs[1])",
                    "striping": f"{world} block-row stripe(s) of a {N_SIDE * world}x{N_SIDE} image, no halo, no collective",
                    "l2": "inputs larger than L2: 4 rotating in/out pairs, 2 GiB working set vs 126 MB L2",
+                   "launch": "K back-to-back launches on one stream; consecutive launches overlap tail and set-up through "
+                             "programmatic dependent launch (each kernel waits for its predecessor before touching memory)",
                    "kernel_path": kernel_path},
         "roofline": roofline, "e2e": e2e, "gpu_launches": timed_launches, "clocks": clocks,
     }
