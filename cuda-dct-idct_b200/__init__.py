@@ -21,6 +21,7 @@ from .api import (  # noqa: F401
     lib_path,
     metrics,
     roundtrip,
+    roundtrip_any,
     roundtrip_host,
     roundtrip_with_metrics,
     zigzag_mask,
@@ -32,5 +33,5 @@ from .stripes import stripe_rows  # noqa: F401
 __all__ = [
     "ALL_COEFFS", "B200DCTError", "Plan", "build", "dct_all_blocks", "dct_all_blocks_cuda", "forward",
     "idct_all_blocks", "idct_all_blocks_cuda", "inverse", "lib", "lib_path", "metrics", "roundtrip",
-    "roundtrip_host", "roundtrip_with_metrics", "stripe_rows", "zigzag_mask",
+    "roundtrip_any", "roundtrip_host", "roundtrip_with_metrics", "stripe_rows", "zigzag_mask",
 ]

@@ -62,6 +62,7 @@ def lib() -> C.CDLL:
         L.b200dct_metrics_workspace_bytes.argtypes = [i, i]
         L.b200dct_metrics_workspace_bytes.restype = sz
         L.b200dct_roundtrip_metrics.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp, vp, sz, vp]
+        L.b200dct_roundtrip_any.argtypes = [vp, vp, i, sz, vp, sz, i, i, vp]
         L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
         L.b200dct_metrics_accumulate.argtypes = [vp, vp, i, sz, i, i, vp, vp]
         L.b200dct_time_calls.argtypes = [vp, i, vp, i, sz, vp, i, sz, vp, i, sz, i, i, i, C.POINTER(C.c_float), vp]
@@ -237,6 +238,24 @@ def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None):
     with torch.cuda.device(img.device):
         _check(lib().b200dct_roundtrip(_plan(plan)._h, ip, idt, ipitch, op, odt, opitch, cp, cdt, cpitch, H, W,
                                        _stream(stream)))
+    return out
+
+
+def roundtrip_any(img, out=None, plan: Plan | None = None, stream=None):
+    """Round trip of a 2-d CUDA tensor of ANY height/width/alignment (ragged edges are padded by
+    edge replication and cropped back; aligned multiples of 8 take the fast path)."""
+    import torch
+
+    if not (img.is_cuda and img.dim() == 2 and img.stride(1) == 1):
+        raise B200DCTError("expected a row-major 2-d CUDA tensor")
+    if out is None:
+        out = torch.empty_like(img)
+    if out.shape != img.shape or out.dtype != img.dtype or out.stride(1) != 1:
+        raise B200DCTError("out must match img")
+    with torch.cuda.device(img.device):
+        _check(lib().b200dct_roundtrip_any(_plan(plan)._h, img.data_ptr(), _dt(img), img.stride(0) * img.element_size(),
+                                           out.data_ptr(), out.stride(0) * out.element_size(), img.shape[0], img.shape[1],
+                                           _stream(stream)))
     return out
 
 

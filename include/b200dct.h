@@ -130,6 +130,16 @@ int b200dct_roundtrip(const b200dct_plan *plan,
                       void *coef_or_null, b200dct_dtype coef_dt, size_t coef_pitch,
                       int H, int W, void *stream);
 
+/* Round trip for ANY image: H and W need not be multiples of 8 and nothing needs to be aligned
+ * (SURVEY.md section 8f "generality"; the reference silently computes garbage there,
+ * main_newAppr.cu:261-262).  Aligned multiples of 8 go straight to b200dct_roundtrip; anything
+ * else is padded to whole blocks by edge replication into a stream-ordered scratch image
+ * (cudaMallocAsync), transformed, and cropped back: two small extra kernels and 3x the traffic,
+ * but never a wrong answer.  img/out: DEVICE pointers, F32 or U8 (same dtype), H <= 65528 on
+ * the padded path. */
+int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, b200dct_dtype dt, size_t in_pitch,
+                          void *out, size_t out_pitch, int H, int W, void *stream);
+
 /* Fused round trip + quality metrics in the same pass: besides the
  * pixels (and optional coefficients) the kernel accumulates, between the pixels it read and
  * the pixels it wrote (as stored: u8 after clamp+truncate, f32 unclamped),

@@ -369,3 +369,23 @@ def test_in_place_calls(dct, oracle, path):
     u8 = dev(img.astype(np.uint8))
     dct.roundtrip(u8, out=u8, plan=plan)
     assert np.array_equal(host(u8), oracle.roundtrip(img.astype(np.uint8)))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (7, 9), (100, 203), (64, 70), (37, 256), (256, 256), (1081, 1923)])
+@pytest.mark.parametrize("u8", [False, True])
+def test_any_size_round_trip(dct, oracle, shape, u8):
+    """b200dct_roundtrip_any: ragged sizes are padded by edge replication to whole blocks,
+    transformed and cropped; equals the oracle applied to the np.pad(mode='edge') image."""
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = rng.integers(0, 256, shape).astype(np.uint8 if u8 else np.float32)
+    H, W = shape
+    padded = np.pad(img, ((0, -H % 8), (0, -W % 8)), mode="edge")
+    want = oracle.roundtrip(np.ascontiguousarray(padded))[:H, :W]
+    got = host(dct.roundtrip_any(dev(img)))
+    assert np.array_equal(got, want) if u8 else np.array_equal(bits(got), bits(want))
+    # unaligned views of an aligned size take the padded path too and stay exact
+    if H % 8 == 0 and W % 8 == 0 and W >= 16:
+        big = torch.zeros(H, W + 3, dtype=torch.uint8 if u8 else torch.float32, device="cuda")
+        big[:, 1:W + 1] = dev(img)
+        got = host(dct.roundtrip_any(big[:, 1:W + 1]))
+        assert np.array_equal(got, want) if u8 else np.array_equal(bits(got), bits(want))

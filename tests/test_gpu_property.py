@@ -117,3 +117,35 @@ def test_cuda_graph_capture(dct, oracle, path, expect):
     assert torch.equal(out.view(torch.int32), want.view(torch.int32))
     band = host(img[:16])
     assert np.array_equal(bits(host(out[:16])), bits(oracle.roundtrip(band)))
+
+
+def test_host_threads_are_reentrant(dct, oracle):
+    """The C ABI is re-entrant: four host threads, each with its own plan and stream, hammer the
+    library concurrently (ctypes releases the GIL); every result stays exact."""
+    import threading
+
+    imgs = [oracle.rand_image(1024, 1024, 100 + i) for i in range(4)]
+    wants = [oracle.roundtrip(x, keep=oracle.zigzag_mask(6 + i)) for i, x in enumerate(imgs)]
+    errors = []
+
+    def worker(i):
+        try:
+            torch.cuda.set_device(0)
+            plan = dct.Plan(keep=oracle.zigzag_mask(6 + i), path=1 + (i % 2))
+            s = torch.cuda.Stream()
+            x = torch.from_numpy(imgs[i]).cuda()
+            y = torch.empty_like(x)
+            for _ in range(50):
+                dct.roundtrip(x, out=y, plan=plan, stream=s)
+            s.synchronize()
+            if not np.array_equal(bits(y.cpu().numpy()), bits(wants[i])):
+                errors.append(f"thread {i}: mismatch")
+        except Exception as e:  # pragma: no cover
+            errors.append(f"thread {i}: {e!r}")
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
