@@ -636,8 +636,10 @@ extern "C" int b200dct_roundtrip_host(const b200dct_plan *plan, const void *h_in
     if (cudaGetDevice(&dev) != cudaSuccess) return B200DCT_ERR_NODEVICE;
     const size_t es = elem_size((int)in_dt);
     const size_t row = (size_t)W * es;
-    // ~16 MiB chunks (env B200DCT_HOST_CHUNK_MB; measured best of 2..32 MiB on B200, round 1), at least 8 rows, whole block-rows: small
-    // enough that the un-overlapped first H2D / last D2H are a few percent of the transfer
+    // ~16 MiB chunks (env B200DCT_HOST_CHUNK_MB; best of 2..32 MiB on B200), at least 8 rows, whole
+    // block-rows.  PCIe Gen5 on the box: H2D alone 55.5 GB/s, D2H alone 57.2, both at once 49.8
+    // each; this pipeline sustains 43.4 GB/s each way (profiles/r01_pcie.txt).  Shorter chunks at
+    // both ends were tried and changed nothing.
     static int chunk_mb = 0;
     if (!chunk_mb) {
         const char *e = getenv("B200DCT_HOST_CHUNK_MB");

@@ -129,7 +129,7 @@ __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
 // P.partials[cta]; k_reduce_partials then adds them up in a fixed order (deterministic).
 // The input row is re-read at the end (an L2 hit) instead of being kept in 64 registers.
 template <int MODE, bool SPARSE, int QMODE, int PIX, bool METRICS = false>
-__global__ void __launch_bounds__(128) k_direct(const __grid_constant__ DirectParams P)
+__global__ void __launch_bounds__(128, METRICS ? 4 : 1) k_direct(const __grid_constant__ DirectParams P)
 {
     // CTA = 32 block-columns x 4 block-rows; grid.x walks block-rows (no 65535 limit),
     // grid.y walks groups of 32 block-columns.  Lanes of a warp are horizontally adjacent
