@@ -119,9 +119,10 @@ struct DenseT {
 //   inverse  column pass: M[y][x] = sum_i T[i][y] D[i][x]   -> at(y,i) = T[i][y]
 //   inverse  row    pass: R[y][x] = sum_i M[y][i] T[i][x]   -> at(x,i) = T[i][x]
 // so the inverse is the forward machinery with T transposed.
-template <bool INV>
+template <bool INV, bool CBANK = false>
 struct HaweelT {
     static constexpr bool is_static = true;
+    static constexpr bool cbank_pairs = CBANK;
     __host__ __device__ static constexpr float at(int a, int i) { return INV ? haweel(i, a) : haweel(a, i); }
     // row-pass output pairing: columns with identical sparsity patterns share an FFMA2
     static constexpr int n_units = INV ? 4 : 5;
@@ -140,6 +141,7 @@ struct HaweelT {
 template <bool INV>
 struct RuntimeT {
     static constexpr bool is_static = false;
+    static constexpr bool cbank_pairs = false;
     const DenseT &m;
     __device__ __forceinline__ explicit RuntimeT(const DenseT &mm) : m(mm) {}
     __device__ __forceinline__ float at(int a, int i) const { return INV ? m.tt[a * 8 + i] : m.t[a * 8 + i]; }
@@ -153,6 +155,24 @@ struct RuntimeT {
     __host__ __device__ static constexpr int ua(int k) { return 2 * k; }
     __host__ __device__ static constexpr int ub(int k) { return 2 * k + 1; }
 };
+
+// The five unequal constant pairs of the row passes can live in the constant bank: ptxas then
+// fetches them once with LDCU into uniform register pairs (FFMA2 takes UR pairs as operands)
+// instead of rebuilding them from immediates with MOVs all over the unrolled code: -100
+// instructions per block (1784 -> 1680 in the f32 round trip), same bits.  Measured on one B200
+// (profiles/r01_pair_constants.txt): issue-bound kernels gain (u8 direct 70.7 -> 65.4 us, f32
+// direct 92.0 -> 88.0), the HBM-bound f32 TMA kernel loses 0.9 % (81.8 -> 82.5), so the policy
+// is a template parameter (HaweelT<INV, CBANK>).
+static __constant__ float2 c_pairs[5] = {{(float)0.35355339, -(float)0.35355339}, {(float)0.5, -(float)0.5},
+                                  {(float)0.4472136, (float)0.2236068}, {(float)0.2236068, -(float)0.4472136},
+                                  {(float)0.70710678, -(float)0.70710678}};
+__host__ __device__ constexpr int pair_index(float na, float nb)
+{
+    return (na == (float)0.35355339) ? 0 : (na == (float)0.5) ? 1 : (na == (float)0.4472136) ? 2
+         : (na == (float)0.2236068) ? 3 : 4;
+}
+template <int I>
+__device__ __forceinline__ float2 pair_constant() { return c_pairs[I]; }
 
 // ---------------------------------------------------------------- the two passes
 // Column pass, in place: for each column pair j, p[y][j] <- chain_i at(y,i) * p[i][j].
@@ -195,7 +215,8 @@ __device__ __forceinline__ void row_pass(const float (&m)[8], float (&o)[8], con
                         constexpr bool neg = ta < 0.0f || (ta == 0.0f && tb < 0.0f);
                         constexpr float na = neg ? -ta : ta, nb = neg ? -tb : tb;
                         const float mm = neg ? -m[IC(i)] : m[IC(i)];
-                        acc = ffma2(bc(mm), make_float2(na, nb), acc);
+                        if constexpr (TP::cbank_pairs && na != nb) acc = ffma2(bc(mm), pair_constant<pair_index(na, nb)>(), acc);
+                        else acc = ffma2(bc(mm), make_float2(na, nb), acc);
                     }
                 } else {
                     acc = ffma2(bc(m[IC(i)]), tp.at2(xa, IC(i)), acc);

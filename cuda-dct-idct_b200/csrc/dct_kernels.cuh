@@ -51,17 +51,17 @@ struct QSel<Q_PARAM_DIV> {
 
 // Runs the selected stages on a block held in p.
 //   FWD: pixels-128 -> C      INV: C -> R      RT: pixels-128 -> (C via emit_coef) -> R
-template <int MODE, bool SPARSE, int QMODE, class EmitCoef>
+template <int MODE, bool SPARSE, int QMODE, bool CBANK, class EmitCoef>
 __device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams &cp, EmitCoef &&emit_coef)
 {
     auto qp = QSel<QMODE>::make(cp.q);
     if constexpr (MODE != MODE_INV) {
-        if constexpr (SPARSE) forward_block(p, HaweelT<false>{}, qp);
+        if constexpr (SPARSE) forward_block(p, HaweelT<false, CBANK>{}, qp);
         else forward_block(p, RuntimeT<false>(cp.t), qp);
     }
     if constexpr (MODE == MODE_RT) emit_coef(p);
     if constexpr (MODE != MODE_FWD) {
-        if constexpr (SPARSE) inverse_block(p, HaweelT<true>{}, qp);
+        if constexpr (SPARSE) inverse_block(p, HaweelT<true, CBANK>{}, qp);
         else inverse_block(p, RuntimeT<true>(cp.t), qp);
     }
 }
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : 1) k_direct(const __grid_co
         }
     };
 
-    run_block<MODE, SPARSE, QMODE>(p, P.cp, [&](float2 (&c)[8][4]) {
+    run_block<MODE, SPARSE, QMODE, true>(p, P.cp, [&](float2 (&c)[8][4]) {
         if (P.coef && valid) store_coef(P.coef, P.coef_pitch, c);
         if constexpr (METRICS) {
             sfor<8>([&](auto r) {
@@ -509,7 +509,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             }
         };
 
-        run_block<MODE, SPARSE, QMODE>(p, P.cp, [&](float2 (&c)[8][4]) {
+        run_block<MODE, SPARSE, QMODE, (MODE == MODE_INV ? false : PIX == DT_U8)>(p, P.cp, [&](float2 (&c)[8][4]) {
             if (P.has_coef) put_coef_tile(&P.coef_map, c);
         });
 
