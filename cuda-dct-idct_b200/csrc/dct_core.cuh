@@ -161,8 +161,10 @@ struct RuntimeT {
 // instead of rebuilding them from immediates with MOVs all over the unrolled code: -100
 // instructions per block (1784 -> 1680 in the f32 round trip), same bits.  Measured on one B200
 // (profiles/r01_pair_constants.txt): issue-bound kernels gain (u8 direct 70.7 -> 65.4 us, f32
-// direct 92.0 -> 88.0), the HBM-bound f32 TMA kernel loses 0.9 % (81.8 -> 82.5), so the policy
-// is a template parameter (HaweelT<INV, CBANK>).
+// direct 92.0 -> 88.0); the HBM-bound f32 TMA kernel is 0.9 % slower in a short burst (81.8 ->
+// 82.5 us) but 1.3 % faster over 4000 power-capped launches (83.7 -> 82.6 us: fewer instructions,
+// less power, same clocks), which is the regime that counts.  All kernels use it; the policy
+// stays a template parameter (HaweelT<INV, CBANK>).
 static __constant__ float2 c_pairs[5] = {{(float)0.35355339, -(float)0.35355339}, {(float)0.5, -(float)0.5},
                                   {(float)0.4472136, (float)0.2236068}, {(float)0.2236068, -(float)0.4472136},
                                   {(float)0.70710678, -(float)0.70710678}};

@@ -509,7 +509,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             }
         };
 
-        run_block<MODE, SPARSE, QMODE, (MODE == MODE_INV ? false : PIX == DT_U8)>(p, P.cp, [&](float2 (&c)[8][4]) {
+        run_block<MODE, SPARSE, QMODE, true>(p, P.cp, [&](float2 (&c)[8][4]) {
             if (P.has_coef) put_coef_tile(&P.coef_map, c);
         });
 
