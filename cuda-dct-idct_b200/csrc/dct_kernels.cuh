@@ -128,8 +128,15 @@ __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
 // clamp+truncate) and the number of non-zero quantised coefficients, and writes them to
 // P.partials[cta]; k_reduce_partials then adds them up in a fixed order (deterministic).
 // The input row is re-read at the end (an L2 hit) instead of being kept in 64 registers.
+// Occupancy of the direct family: 5 CTAs of 128 threads per SM (<= 96 registers, 24-40 bytes of
+// spill) instead of the 4 that the unconstrained 128 registers allow.  Same box, 8192^2
+// (profiles/r01_direct_occupancy.txt): dense-T round trip 108.2 -> 92.4 us, f32 87.7 -> 85.9,
+// u8 65.3 -> 65.3; 6 CTAs (80 registers, up to 400 bytes of spill) loses everywhere.
+#ifndef B200DCT_DIRECT_MIN_BLOCKS
+#define B200DCT_DIRECT_MIN_BLOCKS 5
+#endif
 template <int MODE, bool SPARSE, int QMODE, int PIX, bool METRICS = false>
-__global__ void __launch_bounds__(128, METRICS ? 4 : 1) k_direct(const __grid_constant__ DirectParams P)
+__global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) k_direct(const __grid_constant__ DirectParams P)
 {
     // CTA = 32 block-columns x 4 block-rows; grid.x walks block-rows (no 65535 limit),
     // grid.y walks groups of 32 block-columns.  Lanes of a warp are horizontally adjacent
