@@ -318,7 +318,7 @@ uint32_t *sched_slot()
 } // namespace
 
 static bool tma_dynamic = true; // env B200DCT_TMA_STATIC=1 forces the static tile split
-static int tma_warps = B200DCT_TMA_DEFAULT_WARPS; // warps per CTA of the persistent kernel (env B200DCT_TMA_WARPS, 1..TMA_MAX_WARPS)
+static int tma_warps = 0; // env B200DCT_TMA_WARPS: warps per CTA of the persistent kernel (0 = per-flavour default; clamped to the kernel's CTA size and to shared memory)
 static int tma_max_run = 2;                       // env B200DCT_TMA_RUN: longest run of tiles per claim
 // Programmatic dependent launch (default on; env B200DCT_PDL=0 turns it off): consecutive kernels
 // of this library in one stream overlap the next kernel's CTA launch and set-up with the previous
@@ -383,7 +383,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         static std::once_flag once;
         std::call_once(once, [] {
             const char *e = getenv("B200DCT_TMA_WARPS");
-            if (e && atoi(e) >= 1 && atoi(e) <= TMA_MAX_WARPS) tma_warps = atoi(e);
+            if (e && atoi(e) >= 1 && atoi(e) <= 32) tma_warps = atoi(e);
             const char *r = getenv("B200DCT_TMA_RUN");
             if (r && atoi(r) >= 1 && atoi(r) <= 4096) tma_max_run = atoi(r);
             const char *g = getenv("B200DCT_TMA_GRID");
@@ -406,8 +406,18 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         // a captured launch may be replayed concurrently with anything: static split there
         if (tma_dynamic && !capturing) P.sched = sched_slot();
         P.cp = pl->cp;
-        const int nw = tma_warps;
-        const size_t smem = (size_t)nw * WARP_SMEM_BYTES + (size_t)nw * 8 + 1024;
+        // tile buffers as large as the largest tile image among the planes of this call
+        uint32_t buf = tile_bytes_of(in.dt) > tile_bytes_of(out.dt) ? tile_bytes_of(in.dt) : tile_bytes_of(out.dt);
+        if (coef.ptr && tile_bytes_of(coef.dt) > buf) buf = tile_bytes_of(coef.dt);
+        P.buf_bytes = buf;
+        // warps per CTA: the flavour's CTA size (8 for sparse-T f32; all the CTA holds for the
+        // FP32-bound u8 and dense-T flavours), limited by 227 KiB of shared memory
+        const int max_w = tma_cta_threads(pix, pl->sparse) / 32;
+        int nw = tma_warps > 0 ? tma_warps : (pix == DT_U8 || !pl->sparse ? max_w : B200DCT_TMA_DEFAULT_WARPS);
+        if (nw > max_w) nw = max_w;
+        const int smem_w = (int)((227u * 1024u - 1024u) / (2u * buf + 8u));
+        if (nw > smem_w) nw = smem_w;
+        const size_t smem = (size_t)nw * 2 * buf + (size_t)nw * 8 + 1024;
         unsigned long long want = (nt + nw - 1) / nw;
         const unsigned long long gcap = (unsigned long long)(tma_grid > 0 ? tma_grid : di.sms);
         const int grid = (int)(want < gcap ? want : gcap);

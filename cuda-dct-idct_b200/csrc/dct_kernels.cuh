@@ -281,11 +281,13 @@ struct TmaParams {
     uint32_t *sched;
     uint32_t run;         // tiles per ticket for the first run_tickets tickets, then 1
     uint32_t run_tickets;
+    uint32_t buf_bytes;   // size of one tile buffer: the largest tile image among the planes of this call
     CommonParams cp;
 };
 
-constexpr int TILE_BUF_BYTES = 8192;
-constexpr int WARP_SMEM_BYTES = 2 * TILE_BUF_BYTES;
+// every warp owns two tile buffers (in, out) of P.buf_bytes each: 8 KiB when an f32 plane is
+// involved, 4 KiB for i16, 2 KiB for an all-u8 round trip
+__host__ __device__ constexpr uint32_t tile_bytes_of(int dt) { return dt == DT_F32 ? 8192u : (dt == DT_I16 ? 4096u : 2048u); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -393,28 +395,35 @@ __device__ __forceinline__ void tile_st_f32(uint32_t buf, uint32_t off0, const f
 template <int DT>
 __device__ __forceinline__ uint32_t tile_bytes()
 {
-    return DT == DT_F32 ? 8192u : (DT == DT_I16 ? 4096u : 2048u);
+    return tile_bytes_of(DT);
 }
 
-// Register budget of the persistent kernel: at most B200DCT_TMA_CTA_THREADS threads per
-// CTA, one CTA per SM.  Measured on B200 at 8192^2 f32 (profiles/r01_tma_warps_sweep.txt):
-// 4 warps 119 us, 6: 96, 7: 90, 8: 84.0, 9: 84.0.  8 warps = 2 per scheduler is enough
-// because every thread carries 64 independent FMA chains.  (With single-tile tickets more
-// warps, or a working set above ~1 GiB, collapsed to 113-118 us: the TMA path's address
-// translation thrashes when every SM touches every 2 MiB page; runs of 2 consecutive tiles
-// per ticket removed that -- profiles/r01_tma_run_scheduler.txt.)
+// Register budget of the persistent kernel: one CTA per SM, CTA size per kernel flavour.
+//  * sparse T, f32 pixels (HBM-bound): 256 threads, <= 255 registers.  Measured on B200 at 8192^2
+//    (profiles/r01_tma_warps_sweep.txt): 4 warps 119 us, 6: 96, 7: 90, 8: 84.0, 9: 84.0.  8 warps =
+//    2 per scheduler is enough because every thread carries 64 independent FMA chains.  (With
+//    single-tile tickets more warps, or a working set above ~1 GiB, collapsed to 113-118 us: the
+//    TMA path's address translation thrashes when every SM touches every 2 MiB page; runs of 2
+//    consecutive tiles per ticket removed that -- profiles/r01_tma_run_scheduler.txt.)
+//  * u8 pixels and dense T (FP32-pipe bound): more, smaller warps -- 512 threads / 128 registers
+//    for u8 (tile buffers are only 2 KiB), 384 threads / 168 registers for dense T.
 #ifndef B200DCT_TMA_CTA_THREADS
 #define B200DCT_TMA_CTA_THREADS 256
+#endif
+#ifndef B200DCT_TMA_CTA_THREADS_U8
+#define B200DCT_TMA_CTA_THREADS_U8 512
+#endif
+#ifndef B200DCT_TMA_CTA_THREADS_DENSE
+#define B200DCT_TMA_CTA_THREADS_DENSE 384
 #endif
 #ifndef B200DCT_TMA_DEFAULT_WARPS
 #define B200DCT_TMA_DEFAULT_WARPS 8
 #endif
-#ifdef B200DCT_TMA_MAXNREG
-#define B200DCT_TMA_BOUNDS __maxnreg__(B200DCT_TMA_MAXNREG)
-#else
-#define B200DCT_TMA_BOUNDS __launch_bounds__(B200DCT_TMA_CTA_THREADS, 1)
-#endif
-constexpr int TMA_MAX_WARPS = B200DCT_TMA_CTA_THREADS / 32;
+__host__ __device__ constexpr int tma_cta_threads(int pix, bool sparse)
+{
+    return pix == DT_U8 ? B200DCT_TMA_CTA_THREADS_U8 : (sparse ? B200DCT_TMA_CTA_THREADS : B200DCT_TMA_CTA_THREADS_DENSE);
+}
+#define B200DCT_TMA_BOUNDS __launch_bounds__(tma_cta_threads(PIX, SPARSE), 1)
 
 template <int MODE, bool SPARSE, int QMODE, int PIX>
 __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
@@ -424,9 +433,9 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
-    const uint32_t in_buf = smem_base + warp * WARP_SMEM_BYTES;
-    const uint32_t out_buf = in_buf + TILE_BUF_BYTES;
-    const uint32_t bar = smem_base + nwarps * WARP_SMEM_BYTES + warp * 8;
+    const uint32_t in_buf = smem_base + warp * 2 * P.buf_bytes;
+    const uint32_t out_buf = in_buf + P.buf_bytes;
+    const uint32_t bar = smem_base + nwarps * 2 * P.buf_bytes + warp * 8;
     const uint32_t off0 = f32_tile_off0(lane);
 
     // Dynamic tile scheduler.  The two dies / far and near L2 slices make SMs progress at
