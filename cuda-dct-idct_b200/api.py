@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ALL_COEFFS = (1 << 64) - 1
 
-F32, U8, I16 = 0, 1, 2
+F32, U8, I16, I16_ZIGZAG = 0, 1, 2, 3
 PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
 
 
@@ -189,6 +189,23 @@ def _plane(t):
     return t.data_ptr(), _dt(t), t.stride(0) * t.element_size(), t.shape[0], t.shape[1]
 
 
+def _zz_plane(t):
+    """(ptr, dtype code, pitch bytes, H, W) of a zig-zag coefficient stream: an int16 CUDA tensor of
+    shape (H/8, W/8, 64) -- block-major, 64 coefficients per block in JPEG zig-zag order."""
+    import torch
+
+    if not (t.is_cuda and t.dtype == torch.int16 and t.dim() == 3 and t.shape[2] == 64
+            and t.stride(2) == 1 and t.stride(1) == 64):
+        raise B200DCTError("zig-zag streams are int16 CUDA tensors of shape (H/8, W/8, 64)")
+    return t.data_ptr(), I16_ZIGZAG, t.stride(0) * 2, t.shape[0] * 8, t.shape[1] * 8
+
+
+def empty_zigzag(H: int, W: int, device):
+    import torch
+
+    return torch.empty((H // 8, W // 8, 64), dtype=torch.int16, device=device)
+
+
 def _stream(stream):
     import torch
 
@@ -196,35 +213,38 @@ def _stream(stream):
     return C.c_void_p(s.cuda_stream)
 
 
-def forward(img, coef=None, plan: Plan | None = None, coef_dtype=None, shifted=None, stream=None):
-    """coef = round(T.(img-128).T^T / Q); img f32|u8 CUDA tensor; coef f32 (default) or int16."""
+def forward(img, coef=None, plan: Plan | None = None, coef_dtype=None, shifted=None, stream=None, zigzag=False):
+    """coef = round(T.(img-128).T^T / Q); img f32|u8 CUDA tensor; coef f32 (default) or int16 plane,
+    or (zigzag=True) the block-major int16 zig-zag stream of shape (H/8, W/8, 64)."""
     import torch
 
     ip, idt, ipitch, H, W = _plane(img)
     if coef is None:
-        coef = torch.empty(img.shape, dtype=coef_dtype or torch.float32, device=img.device)
-    cp, cdt, cpitch, _, _ = _plane(coef)
+        coef = empty_zigzag(H, W, img.device) if zigzag else torch.empty(img.shape, dtype=coef_dtype or torch.float32, device=img.device)
+    cp, cdt, cpitch, _, _ = _zz_plane(coef) if zigzag else _plane(coef)
     sp = _plane(shifted)[0] if shifted is not None else None
     with torch.cuda.device(img.device):
         _check(lib().b200dct_forward(_plan(plan)._h, ip, idt, ipitch, cp, cdt, cpitch, sp, H, W, _stream(stream)))
     return coef
 
 
-def inverse(coef, img=None, plan: Plan | None = None, img_dtype=None, stream=None):
-    """img = T^T.(coef*Q).T + 128; coef f32|int16; img f32 (unclamped) or u8 (clamp+truncate)."""
+def inverse(coef, img=None, plan: Plan | None = None, img_dtype=None, stream=None, zigzag=False):
+    """img = T^T.(coef*Q).T + 128; coef f32|int16 plane or (zigzag=True) the zig-zag stream;
+    img f32 (unclamped) or u8 (clamp+truncate)."""
     import torch
 
-    cp, cdt, cpitch, H, W = _plane(coef)
+    cp, cdt, cpitch, H, W = _zz_plane(coef) if zigzag else _plane(coef)
     if img is None:
-        img = torch.empty(coef.shape, dtype=img_dtype or torch.float32, device=coef.device)
+        img = torch.empty((H, W) if zigzag else coef.shape, dtype=img_dtype or torch.float32, device=coef.device)
     ip, idt, ipitch, _, _ = _plane(img)
     with torch.cuda.device(coef.device):
         _check(lib().b200dct_inverse(_plan(plan)._h, cp, cdt, cpitch, ip, idt, ipitch, H, W, _stream(stream)))
     return img
 
 
-def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None):
-    """Fused DCT -> quantise -> dequantise -> IDCT in one pass; optional coefficient plane."""
+def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None, zigzag=False):
+    """Fused DCT -> quantise -> dequantise -> IDCT in one pass; optional coefficient plane
+    (zigzag=True: `coef` is the block-major int16 zig-zag stream)."""
     import torch
 
     ip, idt, ipitch, H, W = _plane(img)
@@ -232,7 +252,7 @@ def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None):
         out = torch.empty_like(img)
     op, odt, opitch, _, _ = _plane(out)
     if coef is not None:
-        cp, cdt, cpitch, _, _ = _plane(coef)
+        cp, cdt, cpitch, _, _ = _zz_plane(coef) if zigzag else _plane(coef)
     else:
         cp, cdt, cpitch = None, F32, 0
     with torch.cuda.device(img.device):

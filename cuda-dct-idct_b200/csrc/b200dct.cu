@@ -229,12 +229,13 @@ static encode_tiled_fn get_encode()
     return fn;
 }
 
-static size_t elem_size(int dt) { return dt == DT_F32 ? 4 : (dt == DT_I16 ? 2 : 1); }
+static size_t elem_size(int dt) { return dt == DT_F32 ? 4 : ((dt == DT_I16 || dt == DT_I16ZZ) ? 2 : 1); }
 
 // Can this plane be addressed by the tile view of its dtype?
 static bool tma_plane_ok(const void *ptr, int dt, size_t pitch, int W)
 {
     if (((uintptr_t)ptr & 15) || (pitch & 15)) return false;
+    if (dt == DT_I16ZZ) return false; // the block-major zig-zag stream is written by the direct family
     if (dt == DT_F32) return (W % 32) == 0;
     return (((size_t)W * elem_size(dt)) % 16) == 0;
 }
@@ -281,8 +282,9 @@ struct Plane {
 static int check_plane(const Plane &pl, int W, bool pixels)
 {
     if (!pl.ptr) return B200DCT_ERR_ARG;
-    if (pixels ? (pl.dt != DT_F32 && pl.dt != DT_U8) : (pl.dt != DT_F32 && pl.dt != DT_I16)) return B200DCT_ERR_ARG;
-    if (pl.pitch < (size_t)W * elem_size(pl.dt)) return B200DCT_ERR_SHAPE;
+    if (pixels ? (pl.dt != DT_F32 && pl.dt != DT_U8) : (pl.dt != DT_F32 && pl.dt != DT_I16 && pl.dt != DT_I16ZZ)) return B200DCT_ERR_ARG;
+    // zig-zag stream: pitch = bytes per block-row = (W/8) blocks x 128 B (= 8 image rows x W x 2 B)
+    if (pl.pitch < (size_t)W * elem_size(pl.dt) * (pl.dt == DT_I16ZZ ? 8 : 1)) return B200DCT_ERR_SHAPE;
     const size_t a = pl.dt == DT_U8 ? 8 : 16;
     if (((uintptr_t)pl.ptr % a) || (pl.pitch % a)) return B200DCT_ERR_ALIGN;
     return B200DCT_OK;

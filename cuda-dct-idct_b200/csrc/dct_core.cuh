@@ -361,6 +361,24 @@ __device__ __forceinline__ uint32_t pack2_i16(float a, float b)
     asm("cvt.rni.sat.s16.f32 %0, %1;" : "=h"(ib) : "f"(b));
     return ((uint32_t)(unsigned short)ia) | ((uint32_t)(unsigned short)ib << 16);
 }
+// JPEG zig-zag scan (ITU-T T.81 figure 5): position k of the scan -> row*8+col of the block.
+__host__ __device__ constexpr int zigzag_pos(int k)
+{
+    constexpr unsigned char zz[64] = {
+        0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5,
+        12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+        35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51,
+        58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return zz[k];
+}
+// the register holding scan position K of a block kept as p[row][column pair]
+template <int K>
+__device__ __forceinline__ float &zigzag_elem(float2 (&p)[8][4])
+{
+    constexpr int rc = zigzag_pos(K), r = rc >> 3, c = rc & 7;
+    if constexpr (c & 1) return p[r][c >> 1].y;
+    else return p[r][c >> 1].x;
+}
 __device__ __forceinline__ float i16_lo(uint32_t w) { return (float)(short)(w & 0xffffu); }
 __device__ __forceinline__ float i16_hi(uint32_t w) { return (float)((int)w >> 16); }
 

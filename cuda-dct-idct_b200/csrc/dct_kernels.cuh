@@ -21,7 +21,9 @@
 namespace b200dct {
 
 enum { MODE_FWD = 0, MODE_INV = 1, MODE_RT = 2 };
-enum { DT_F32 = 0, DT_U8 = 1, DT_I16 = 2, DT_NONE = -1 };
+// DT_I16ZZ: compact coefficient stream, block-major -- block (r, c) of the H/8 x W/8 grid is 64
+// consecutive int16 in JPEG zig-zag order at byte offset r*pitch + c*128 (direct family only)
+enum { DT_F32 = 0, DT_U8 = 1, DT_I16 = 2, DT_I16ZZ = 3, DT_NONE = -1 };
 // quantiser variants: 0 = JPEG immediates, all kept; 1 = parameter tables, fast exact
 // division, mask applied; 2 = parameter tables, __fdiv_rn (divisors outside the proven set)
 enum { Q_IMM = 0, Q_PARAM = 1, Q_PARAM_DIV = 2 };
@@ -118,6 +120,29 @@ __device__ __forceinline__ void unpack_i16(uint4 w, float2 (&r)[4])
     r[0] = make_float2(i16_lo(w.x), i16_hi(w.x)); r[1] = make_float2(i16_lo(w.y), i16_hi(w.y));
     r[2] = make_float2(i16_lo(w.z), i16_hi(w.z)); r[3] = make_float2(i16_lo(w.w), i16_hi(w.w));
 }
+// block <-> 128 contiguous bytes of zig-zag ordered int16 (8 x 128-bit accesses per thread;
+// adjacent lanes are adjacent blocks, so a warp covers one contiguous 4 KiB span)
+__device__ __forceinline__ void st_block_zigzag(void *base, float2 (&c)[8][4])
+{
+    sfor<8>([&](auto g) {
+        uint4 w;
+        w.x = pack2_i16(zigzag_elem<8 * IC(g) + 0>(c), zigzag_elem<8 * IC(g) + 1>(c));
+        w.y = pack2_i16(zigzag_elem<8 * IC(g) + 2>(c), zigzag_elem<8 * IC(g) + 3>(c));
+        w.z = pack2_i16(zigzag_elem<8 * IC(g) + 4>(c), zigzag_elem<8 * IC(g) + 5>(c));
+        w.w = pack2_i16(zigzag_elem<8 * IC(g) + 6>(c), zigzag_elem<8 * IC(g) + 7>(c));
+        reinterpret_cast<uint4 *>(base)[IC(g)] = w;
+    });
+}
+__device__ __forceinline__ void ld_block_zigzag(const void *base, float2 (&c)[8][4])
+{
+    sfor<8>([&](auto g) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(base) + IC(g));
+        zigzag_elem<8 * IC(g) + 0>(c) = i16_lo(w.x); zigzag_elem<8 * IC(g) + 1>(c) = i16_hi(w.x);
+        zigzag_elem<8 * IC(g) + 2>(c) = i16_lo(w.y); zigzag_elem<8 * IC(g) + 3>(c) = i16_hi(w.y);
+        zigzag_elem<8 * IC(g) + 4>(c) = i16_lo(w.z); zigzag_elem<8 * IC(g) + 5>(c) = i16_hi(w.z);
+        zigzag_elem<8 * IC(g) + 6>(c) = i16_lo(w.w); zigzag_elem<8 * IC(g) + 7>(c) = i16_hi(w.w);
+    });
+}
 __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
 {
     sfor<4>([&](auto j) { r[IC(j)] = fadd2(r[IC(j)], bc(s)); });
@@ -162,6 +187,8 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch;
         if (P.coef_dt == DT_F32) {
             sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+        } else if (P.coef_dt == DT_I16ZZ) { // pitch = bytes per block-row of the stream
+            ld_block_zigzag((const char *)P.in + (size_t)by * P.in_pitch + (size_t)bxi * 128, p);
         } else {
             sfor<8>([&](auto r) {
                 unpack_i16(__ldg(reinterpret_cast<const uint4 *>(src + IC(r) * P.in_pitch + (size_t)bxi * 16)), p[IC(r)]);
@@ -188,6 +215,8 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         char *dst = (char *)plane + (size_t)by * 8 * pitch;
         if (P.coef_dt == DT_F32) {
             sfor<8>([&](auto r) { st_row_f32(dst + IC(r) * pitch + (size_t)bxi * 32, c[IC(r)]); });
+        } else if (P.coef_dt == DT_I16ZZ) {
+            st_block_zigzag((char *)plane + (size_t)by * pitch + (size_t)bxi * 128, c);
         } else {
             sfor<8>([&](auto r) {
                 *reinterpret_cast<uint4 *>(dst + IC(r) * pitch + (size_t)bxi * 16) = pack_i16(c[IC(r)]);

@@ -53,7 +53,13 @@ extern "C" {
 typedef enum b200dct_dtype {
     B200DCT_F32 = 0, /* float pixels / integer-valued float coefficients (the reference's type) */
     B200DCT_U8 = 1,  /* 8-bit pixels: convertToFloat on load, clamp+truncate on store (utils.cu:10-24) */
-    B200DCT_I16 = 2  /* compact coefficients (saturating); coefficient planes only */
+    B200DCT_I16 = 2, /* compact coefficients (saturating); coefficient planes only */
+    /* Compact coefficient STREAM (the natural input of an entropy coder):
+     * block-major -- block (r, c) of the H/8 x W/8 grid is 64 consecutive int16 (saturating) in
+     * JPEG zig-zag scan order (ITU-T T.81 figure 5) at byte offset r*pitch + c*128.  `pitch` is
+     * the bytes per BLOCK-ROW of the stream (>= (W/8)*128, multiple of 16).  Coefficient role
+     * only (forward output, inverse input, round-trip coefficient output); direct kernel family. */
+    B200DCT_I16_ZIGZAG = 3
 } b200dct_dtype;
 
 enum {

@@ -94,6 +94,32 @@ uint64_t oracle_zigzag_mask(int k)
     return m;
 }
 
+/* Compact coefficient stream (not in the reference, whose coefficient
+ * plane is a float image, main_newAppr.cu:99-103): block-major, block (r,c) -> 64 consecutive
+ * int16 in zig-zag order, values = the integer-valued float coefficients saturated to int16. */
+void oracle_zigzag_i16(const float *coef, int H, int W, int16_t *out)
+{
+    const int bx = W / BS;
+    for (int r = 0; r < H / BS; r++)
+        for (int c = 0; c < bx; c++)
+            for (int k = 0; k < 64; k++) {
+                float v = coef[(size_t)(r * BS + k_zigzag[k] / BS) * W + c * BS + k_zigzag[k] % BS];
+                if (v > 32767.0f) v = 32767.0f;
+                if (v < -32768.0f) v = -32768.0f;
+                out[((size_t)r * bx + c) * 64 + k] = (int16_t)lrintf(v);
+            }
+}
+/* and back: the float coefficient plane the inverse transform starts from */
+void oracle_unzigzag_i16(const int16_t *in, int H, int W, float *coef)
+{
+    const int bx = W / BS;
+    for (int r = 0; r < H / BS; r++)
+        for (int c = 0; c < bx; c++)
+            for (int k = 0; k < 64; k++)
+                coef[(size_t)(r * BS + k_zigzag[k] / BS) * W + c * BS + k_zigzag[k] % BS] =
+                    (float)in[((size_t)r * bx + c) * 64 + k];
+}
+
 /* Reference input generator: srand(seed); img[i*N+j] = rand()%256
  * (Benchmark_code/benchmark_fastAppr.cu:44-47).  glibc rand(). */
 void oracle_fill_rand(float *img, size_t n, unsigned seed)

@@ -57,6 +57,9 @@ def lib() -> C.CDLL:
         L.oracle_time_roundtrip.restype = C.c_double
         L.oracle_time_roundtrip.argtypes = [f32p, C.c_int, C.c_int, f32p, C.c_int, C.c_int]
         L.oracle_max_threads.restype = C.c_int
+        i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
+        L.oracle_zigzag_i16.argtypes = [f32p, C.c_int, C.c_int, i16p]
+        L.oracle_unzigzag_i16.argtypes = [i16p, C.c_int, C.c_int, f32p]
         _lib = L
     return _lib
 
@@ -77,6 +80,23 @@ def dct2_T() -> np.ndarray:
 
 def zigzag_mask(k: int) -> int:
     return int(lib().oracle_zigzag_mask(k))
+
+
+def zigzag_i16(coef: np.ndarray) -> np.ndarray:
+    """float coefficient plane (H, W) -> block-major int16 zig-zag stream (H/8, W/8, 64)."""
+    coef = np.ascontiguousarray(coef, np.float32)
+    H, W = coef.shape
+    out = np.empty((H // 8, W // 8, 64), np.int16)
+    lib().oracle_zigzag_i16(coef, H, W, out)
+    return out
+
+
+def unzigzag_i16(stream: np.ndarray) -> np.ndarray:
+    stream = np.ascontiguousarray(stream, np.int16)
+    H, W = stream.shape[0] * 8, stream.shape[1] * 8
+    out = np.empty((H, W), np.float32)
+    lib().oracle_unzigzag_i16(stream, H, W, out)
+    return out
 
 
 def rand_image(n_rows: int, n_cols: int, seed: int = 42) -> np.ndarray:

@@ -389,3 +389,36 @@ def test_any_size_round_trip(dct, oracle, shape, u8):
         big[:, 1:W + 1] = dev(img)
         got = host(dct.roundtrip_any(big[:, 1:W + 1]))
         assert np.array_equal(got, want) if u8 else np.array_equal(bits(got), bits(want))
+
+
+@pytest.mark.parametrize("u8", [False, True])
+@pytest.mark.parametrize("shape", [(8, 8), (256, 256), (72, 1056)])
+def test_zigzag_coefficient_stream(dct, oracle, shape, u8):
+    """Compact coefficient stream: block-major int16 in JPEG zig-zag order, written
+    by forward / round trip and read back by inverse; same integers as the coefficient plane."""
+    img = oracle.rand_image_u8(*shape, 7) if u8 else oracle.rand_image(*shape, 7)
+    want_out, want_coef = oracle.roundtrip(img, want_coef=True)
+    want_zz = oracle.zigzag_i16(want_coef)
+    d = dev(img)
+    zz = dct.forward(d, zigzag=True)
+    assert dct.api.last_path() == "direct"
+    assert zz.shape == (shape[0] // 8, shape[1] // 8, 64) and zz.dtype == torch.int16
+    assert np.array_equal(host(zz), want_zz)
+    # the inverse from the stream == the inverse from the plane, bit for bit
+    rec = dct.inverse(zz, zigzag=True, img_dtype=d.dtype)
+    want_rec = oracle.idct(oracle.unzigzag_i16(want_zz))
+    want_rec = oracle.to_u8(want_rec) if u8 else want_rec
+    assert np.array_equal(host(rec), want_rec)
+    if not u8:
+        assert np.array_equal(bits(host(rec)), bits(want_out))
+    # fused round trip that also emits the stream; padded block-row pitch keeps its sentinels
+    bh, bw = shape[0] // 8, shape[1] // 8
+    buf = torch.full((bh, bw + 3, 64), -12345, dtype=torch.int16, device="cuda")
+    out = dct.roundtrip(d, coef=buf[:, :bw, :], zigzag=True)
+    assert np.array_equal(host(out), want_out)
+    got = host(buf)
+    assert np.array_equal(got[:, :bw, :], want_zz)
+    assert (got[:, bw:, :] == -12345).all()
+    # the TMA family does not write this layout: forcing it is an error, never a wrong answer
+    with pytest.raises(dct.B200DCTError):
+        dct.forward(d, zigzag=True, plan=dct.Plan(path=PATHS["tma"]))

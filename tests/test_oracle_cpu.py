@@ -176,3 +176,24 @@ def test_metrics_definition(oracle):
 def test_multithreaded_oracle_matches_sequential(oracle):
     img = oracle.rand_image(128, 128, 9)
     assert np.array_equal(oracle.roundtrip(img, threads=1), oracle.roundtrip(img, threads=4))
+
+
+def test_zigzag_stream_layout(oracle):
+    """The zig-zag scan of the compact coefficient stream is ITU-T T.81's: regenerate it by
+    walking the anti-diagonals and compare; round trip through the stream is lossless for
+    coefficients in int16 range and saturates outside."""
+    order = []
+    for s in range(15):
+        diag = [(r, s - r) for r in range(8) if 0 <= s - r < 8]
+        order += diag if s % 2 else diag[::-1]  # even diagonals run bottom-left -> top-right
+    plane = np.arange(64, dtype=np.float32).reshape(8, 8)
+    assert oracle.zigzag_i16(plane)[0, 0].tolist() == [r * 8 + c for r, c in order]
+    assert [bin(oracle.zigzag_mask(k)).count("1") for k in (6, 10)] == [6, 10]
+    img = oracle.rand_image(16, 24, 3)
+    coef = oracle.dct(img)
+    zz = oracle.zigzag_i16(coef)
+    assert zz.shape == (2, 3, 64)
+    assert np.array_equal(oracle.unzigzag_i16(zz), coef)
+    assert zz[1, 2, 0] == coef[8, 16] and zz[1, 2, 1] == coef[8, 17] and zz[1, 2, 2] == coef[9, 16]
+    big = np.full((8, 8), 1e6, np.float32); big[0, 1] = -1e6
+    assert oracle.zigzag_i16(big)[0, 0, :2].tolist() == [32767, -32768]
