@@ -22,6 +22,8 @@ namespace b200dct {
     cudaError_t launch_tma_##tag(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);
 B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2)
 #undef B200_DECL
+cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_direct_k.cu
+cudaError_t launch_tma_kmask(int k, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
 
 static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
 {
@@ -337,6 +339,15 @@ static bool use_pdl()
     return v == 1;
 }
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
+static bool compiled_masks() // env B200DCT_COMPILED_MASKS=0: retained-coefficient masks as runtime data only (A/B)
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *p = getenv("B200DCT_COMPILED_MASKS");
+        v = (p && atoi(p) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
 
 static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,
                cudaStream_t stream, double *partials = nullptr, double *acc = nullptr)
@@ -380,6 +391,13 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
                    tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
                    (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
     if (pl->path == B200DCT_PATH_TMA && !use_tma) return B200DCT_ERR_ALIGN;
+
+    // retained-coefficient round trips (first k = 6..10 zig-zag coefficients of the default
+    // tables): kernels with the mask as a compile-time constant
+    int kmask = 0;
+    if (mode == MODE_RT && pl->sparse && pl->q_default && pl->q_fastdiv && compiled_masks())
+        for (int k = 6; k <= 10; k++)
+            if (pl->mask == b200dct_zigzag_mask(k)) kmask = k;
 
     if (use_tma) {
         static std::once_flag once;
@@ -427,7 +445,9 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.run = (uint32_t)tma_max_run;
         const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
-        cudaError_t e = launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing);
+        cudaError_t e = (kmask && pix == DT_F32)
+                            ? launch_tma_kmask(kmask, P, grid, nw * 32, smem, stream, use_pdl() && !capturing)
+                            : launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing);
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
         tl_path = "tma";
@@ -459,7 +479,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         tl_path = "direct";
         return B200DCT_OK;
     }
-    e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream, use_pdl() && !capturing);
+    if (kmask) e = launch_direct_kmask(kmask, pix, P, grid, block, stream, use_pdl() && !capturing);
+    else e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream, use_pdl() && !capturing);
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "direct";

@@ -176,9 +176,35 @@ __host__ __device__ constexpr int pair_index(float na, float nb)
 template <int I>
 __device__ __forceinline__ float2 pair_constant() { return c_pairs[I]; }
 
+// ---------------------------------------------------------------- compile-time retained-coefficient masks
+// With the mask known at compile time the dropped coefficients are literal +0.0f: the forward
+// chains that feed only dropped positions are never emitted, and the inverse skips every term
+// whose coefficient is a known zero.  Skipping is exact for the same reason skipping T's zeros
+// is: fma(t, +-0, s) == s bit-for-bit when the running sum s is never -0.0f (it starts at +0.0f),
+// and a chain made only of skipped terms yields the +0.0f it started from.
+template <uint64_t KEEP>
+struct KeepMask {
+    static constexpr uint64_t bits = KEEP;
+    static constexpr bool all = KEEP == ~0ull;
+    __host__ __device__ static constexpr bool kept(int r, int c) { return (KEEP >> (r * 8 + c)) & 1ull; }
+    __host__ __device__ static constexpr bool row_any(int r) { return ((KEEP >> (r * 8)) & 0xffull) != 0; }
+    __host__ __device__ static constexpr bool col_any(int c) { return ((KEEP >> c) & 0x0101010101010101ull) != 0; }
+    __host__ __device__ static constexpr bool pair_any(int r, int j) { return kept(r, 2 * j) || kept(r, 2 * j + 1); }
+};
+using KeepAll = KeepMask<~0ull>;
+// first k positions of the JPEG zig-zag scan (README.md:63 of the reference: 6..10 retained coefficients)
+__host__ __device__ constexpr uint64_t zigzag_prefix_mask(int k)
+{
+    constexpr unsigned char zz[10] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24};
+    uint64_t m = 0;
+    for (int i = 0; i < k && i < 10; i++) m |= 1ull << zz[i];
+    return m;
+}
+
 // ---------------------------------------------------------------- the two passes
 // Column pass, in place: for each column pair j, p[y][j] <- chain_i at(y,i) * p[i][j].
-template <class TP>
+// KM (inverse only): input pairs (row i, pair j) outside the mask are known zeros and skipped.
+template <class TP, class KM = KeepAll>
 __device__ __forceinline__ void col_pass(float2 (&p)[8][4], const TP &tp)
 {
     sfor<4>([&](auto j) {
@@ -189,7 +215,7 @@ __device__ __forceinline__ void col_pass(float2 (&p)[8][4], const TP &tp)
             sfor<8>([&](auto i) {
                 if constexpr (TP::is_static) {
                     constexpr float t = TP::at(IC(y), IC(i));
-                    if constexpr (t != 0.0f) acc = ffma2(in[IC(i)], bc(t), acc);
+                    if constexpr (t != 0.0f && KM::pair_any(IC(i), IC(j))) acc = ffma2(in[IC(i)], bc(t), acc);
                 } else {
                     acc = ffma2(in[IC(i)], bc(tp.at(IC(y), IC(i))), acc);
                 }
@@ -200,17 +226,40 @@ __device__ __forceinline__ void col_pass(float2 (&p)[8][4], const TP &tp)
 }
 
 // Row pass for one row: o[x] <- chain_i m[i] * at(x,i).
-template <class TP>
+// ZIN::zero(i): m[i] is a known zero (skipped); NEED::need(x): o[x] is used at all (a pair of
+// which only one half is needed becomes a scalar chain; unneeded outputs are left untouched).
+struct NoZero { __host__ __device__ static constexpr bool zero(int) { return false; } };
+struct NeedAll { __host__ __device__ static constexpr bool need(int) { return true; } };
+template <class KM> struct ZeroCols { __host__ __device__ static constexpr bool zero(int i) { return !KM::col_any(i); } };
+template <class KM, int Y> struct NeedRow { __host__ __device__ static constexpr bool need(int x) { return KM::kept(Y, x); } };
+
+template <class TP, class ZIN, int X>
+__device__ __forceinline__ float row_chain_scalar(const float (&m)[8], const TP &tp)
+{
+    float acc = 0.0f;
+    sfor<8>([&](auto i) {
+        if constexpr (TP::is_static) {
+            constexpr float t = TP::at(X, IC(i));
+            if constexpr (t != 0.0f && !ZIN::zero(IC(i))) acc = __fmaf_rn(m[IC(i)], t, acc);
+        } else {
+            acc = __fmaf_rn(m[IC(i)], tp.at(X, IC(i)), acc);
+        }
+    });
+    return acc;
+}
+
+template <class TP, class ZIN = NoZero, class NEED = NeedAll>
 __device__ __forceinline__ void row_pass(const float (&m)[8], float (&o)[8], const TP &tp)
 {
     sfor<TP::n_units>([&](auto k) {
         constexpr int xa = TP::ua(IC(k)), xb = TP::ub(IC(k));
-        if constexpr (xb >= 0) {
+        constexpr bool need_a = NEED::need(xa), need_b = xb >= 0 && NEED::need(xb);
+        if constexpr (need_a && need_b) {
             float2 acc = make_float2(0.0f, 0.0f);
             sfor<8>([&](auto i) {
                 if constexpr (TP::is_static) {
                     constexpr float ta = TP::at(xa, IC(i)), tb = TP::at(xb, IC(i));
-                    if constexpr (ta != 0.0f || tb != 0.0f) {
+                    if constexpr ((ta != 0.0f || tb != 0.0f) && !ZIN::zero(IC(i))) {
                         // fma(m,t,c) == fma(-m,-t,c) exactly: normalise the sign of the constant
                         // pair so that only {a,-a},{h,-h},{p,q},{q,-p},{s,-s} ever need registers
                         // (equal halves are broadcast immediates); the sign goes onto m.
@@ -226,17 +275,10 @@ __device__ __forceinline__ void row_pass(const float (&m)[8], float (&o)[8], con
             });
             o[xa] = acc.x;
             o[xb] = acc.y;
-        } else {
-            float acc = 0.0f;
-            sfor<8>([&](auto i) {
-                if constexpr (TP::is_static) {
-                    constexpr float t = TP::at(xa, IC(i));
-                    if constexpr (t != 0.0f) acc = __fmaf_rn(m[IC(i)], t, acc);
-                } else {
-                    acc = __fmaf_rn(m[IC(i)], tp.at(xa, IC(i)), acc);
-                }
-            });
-            o[xa] = acc;
+        } else if constexpr (need_a) {
+            o[xa] = row_chain_scalar<TP, ZIN, xa>(m, tp);
+        } else if constexpr (need_b) {
+            o[xb] = row_chain_scalar<TP, ZIN, xb>(m, tp);
         }
     });
 }
@@ -284,8 +326,10 @@ __device__ __forceinline__ float quantise(float y, int k, const QP &qp)
 }
 
 // ---------------------------------------------------------------- whole-block stages
-// p holds pixels-128 on entry and the quantised coefficients C on exit.
-template <class TF, class QP>
+// p holds pixels-128 on entry and the quantised coefficients C on exit.  KM != KeepAll: the mask
+// is a compile-time constant, dropped coefficients are +0.0f without being computed (the
+// chains that feed only them are dead code) -- same values as computing and masking.
+template <class KM = KeepAll, class TF, class QP>
 __device__ __forceinline__ void forward_block(float2 (&p)[8][4], const TF &tf, const QP &qp)
 {
     col_pass(p, tf);
@@ -295,32 +339,36 @@ __device__ __forceinline__ void forward_block(float2 (&p)[8][4], const TF &tf, c
             m[2 * IC(j)] = p[IC(y)][IC(j)].x;
             m[2 * IC(j) + 1] = p[IC(y)][IC(j)].y;
         });
-        row_pass(m, o, tf);
+        if constexpr (KM::row_any(IC(y))) row_pass<TF, NoZero, NeedRow<KM, IC(y)>>(m, o, tf);
         sfor<4>([&](auto j) {
-            p[IC(y)][IC(j)].x = quantise(o[2 * IC(j)], IC(y) * 8 + 2 * IC(j), qp);
-            p[IC(y)][IC(j)].y = quantise(o[2 * IC(j) + 1], IC(y) * 8 + 2 * IC(j) + 1, qp);
+            if constexpr (KM::kept(IC(y), 2 * IC(j))) p[IC(y)][IC(j)].x = quantise(o[2 * IC(j)], IC(y) * 8 + 2 * IC(j), qp);
+            else p[IC(y)][IC(j)].x = 0.0f;
+            if constexpr (KM::kept(IC(y), 2 * IC(j) + 1)) p[IC(y)][IC(j)].y = quantise(o[2 * IC(j) + 1], IC(y) * 8 + 2 * IC(j) + 1, qp);
+            else p[IC(y)][IC(j)].y = 0.0f;
         });
     });
 }
 
-// p holds quantised coefficients C on entry and R = T^T.(C*Q).T on exit (no +128).
-template <class TI, class QP>
+// p holds quantised coefficients C on entry and R = T^T.(C*Q).T on exit (no +128).  KM != KeepAll
+// promises that every coefficient outside the mask is +-0 (the caller guarantees it: the fused
+// kernels produce them, the inverse-only kernels are not specialised).
+template <class KM = KeepAll, class TI, class QP>
 __device__ __forceinline__ void inverse_block(float2 (&p)[8][4], const TI &ti, const QP &qp)
 {
     sfor<8>([&](auto y) {
         sfor<4>([&](auto j) {
-            p[IC(y)][IC(j)].x *= qp.d(IC(y) * 8 + 2 * IC(j));     // multiply_matrices, utils_kernels.cu:55
-            p[IC(y)][IC(j)].y *= qp.d(IC(y) * 8 + 2 * IC(j) + 1);
+            if constexpr (KM::kept(IC(y), 2 * IC(j))) p[IC(y)][IC(j)].x *= qp.d(IC(y) * 8 + 2 * IC(j)); // multiply_matrices, utils_kernels.cu:55
+            if constexpr (KM::kept(IC(y), 2 * IC(j) + 1)) p[IC(y)][IC(j)].y *= qp.d(IC(y) * 8 + 2 * IC(j) + 1);
         });
     });
-    col_pass(p, ti);
+    col_pass<TI, KM>(p, ti);
     sfor<8>([&](auto y) {
         float m[8], o[8];
         sfor<4>([&](auto j) {
             m[2 * IC(j)] = p[IC(y)][IC(j)].x;
             m[2 * IC(j) + 1] = p[IC(y)][IC(j)].y;
         });
-        row_pass(m, o, ti);
+        row_pass<TI, ZeroCols<KM>, NeedAll>(m, o, ti);
         sfor<4>([&](auto j) { p[IC(y)][IC(j)] = make_float2(o[2 * IC(j)], o[2 * IC(j) + 1]); });
     });
 }

@@ -26,7 +26,9 @@ enum { MODE_FWD = 0, MODE_INV = 1, MODE_RT = 2 };
 enum { DT_F32 = 0, DT_U8 = 1, DT_I16 = 2, DT_I16ZZ = 3, DT_NONE = -1 };
 // quantiser variants: 0 = JPEG immediates, all kept; 1 = parameter tables, fast exact
 // division, mask applied; 2 = parameter tables, __fdiv_rn (divisors outside the proven set)
-enum { Q_IMM = 0, Q_PARAM = 1, Q_PARAM_DIV = 2 };
+// 3..7 = JPEG immediates with the first 6..10 zig-zag coefficients retained, the mask a
+// compile-time constant (README.md:63 of the reference): fused round trips only
+enum { Q_IMM = 0, Q_PARAM = 1, Q_PARAM_DIV = 2, Q_IMM_K6 = 3, Q_IMM_K7 = 4, Q_IMM_K8 = 5, Q_IMM_K9 = 6, Q_IMM_K10 = 7 };
 
 struct CommonParams {
     QuantTables q;
@@ -34,11 +36,13 @@ struct CommonParams {
 };
 
 template <int QMODE>
-struct QSel;
-template <>
-struct QSel<Q_IMM> {
+struct QSel { // Q_IMM and Q_IMM_K6..K10
     using type = QImm;
     __device__ __forceinline__ static QImm make(const QuantTables &) { return QImm{}; }
+};
+template <int QMODE>
+struct KeepOf {
+    using type = KeepMask<(QMODE >= Q_IMM_K6 && QMODE <= Q_IMM_K10) ? zigzag_prefix_mask(QMODE - Q_IMM_K6 + 6) : ~0ull>;
 };
 template <>
 struct QSel<Q_PARAM> {
@@ -57,13 +61,17 @@ template <int MODE, bool SPARSE, int QMODE, bool CBANK, class EmitCoef>
 __device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams &cp, EmitCoef &&emit_coef)
 {
     auto qp = QSel<QMODE>::make(cp.q);
+    // a compile-time mask prunes the forward; the inverse may rely on it only when it consumes
+    // the coefficients this very thread produced (fused round trip)
+    using KM = typename KeepOf<QMODE>::type;
+    static_assert(KM::all || (SPARSE && MODE == MODE_RT), "compile-time masks: sparse fused round trips only");
     if constexpr (MODE != MODE_INV) {
-        if constexpr (SPARSE) forward_block(p, HaweelT<false, CBANK>{}, qp);
+        if constexpr (SPARSE) forward_block<KM>(p, HaweelT<false, CBANK>{}, qp);
         else forward_block(p, RuntimeT<false>(cp.t), qp);
     }
     if constexpr (MODE == MODE_RT) emit_coef(p);
     if constexpr (MODE != MODE_FWD) {
-        if constexpr (SPARSE) inverse_block(p, HaweelT<true, CBANK>{}, qp);
+        if constexpr (SPARSE) inverse_block<KM>(p, HaweelT<true, CBANK>{}, qp);
         else inverse_block(p, RuntimeT<true>(cp.t), qp);
     }
 }

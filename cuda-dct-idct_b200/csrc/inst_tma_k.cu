@@ -1,0 +1,39 @@
+// inst_tma_k.cu -- fused f32 round trips of the TMA family with the retained-coefficient mask
+// (first k = 6..10 zig-zag coefficients, JPEG Q, Haweel's T) as a compile-time constant
+// (see inst_direct_k.cu).
+#include "dct_kernels.cuh"
+
+namespace b200dct {
+
+template <int QM>
+static cudaError_t launch_one(const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl)
+{
+    auto kern = k_tma<MODE_RT, true, QM, DT_F32>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, P);
+}
+
+cudaError_t launch_tma_kmask(int k, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl)
+{
+    switch (k) {
+    case 6: return launch_one<Q_IMM_K6>(P, grid, block, smem, s, pdl);
+    case 7: return launch_one<Q_IMM_K7>(P, grid, block, smem, s, pdl);
+    case 8: return launch_one<Q_IMM_K8>(P, grid, block, smem, s, pdl);
+    case 9: return launch_one<Q_IMM_K9>(P, grid, block, smem, s, pdl);
+    case 10: return launch_one<Q_IMM_K10>(P, grid, block, smem, s, pdl);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace b200dct

@@ -422,3 +422,27 @@ def test_zigzag_coefficient_stream(dct, oracle, shape, u8):
     # the TMA family does not write this layout: forcing it is an error, never a wrong answer
     with pytest.raises(dct.B200DCTError):
         dct.forward(d, zigzag=True, plan=dct.Plan(path=PATHS["tma"]))
+
+
+@pytest.mark.parametrize("k", [6, 7, 8, 9, 10])
+def test_compiled_retained_coefficient_kernels(dct, oracle, k):
+    """k = 6..10 of the default tables run kernels with the mask as a compile-time constant
+    (dead forward chains, skipped zero terms in the inverse): same bits as masking after the
+    fact, on integer, adversarial (ties, -0 coefficients) and non-integer inputs, f32 and u8."""
+    keep = oracle.zigzag_mask(k)
+    plan = dct.Plan(keep=keep, path=PATHS["direct"])
+    for img in (oracle.rand_image(64, 96, k), inputs.adversarial(32), inputs.float_noise(64, 256),
+                inputs.smooth_image(128, 128), -inputs.float_noise(16, 64, 3), np.full((8, 32), 3e5, np.float32)):
+        want_out, want_coef = oracle.roundtrip(img, keep=keep, want_coef=True)
+        coef = torch.empty(img.shape, dtype=torch.float32, device="cuda")
+        out = dct.roundtrip(dev(img), coef=coef, plan=plan)
+        assert dct.api.last_path() == "direct"
+        assert np.array_equal(bits(host(coef)), bits(want_coef))
+        assert np.array_equal(bits(host(out)), bits(want_out))
+        assert np.array_equal(bits(host(dct.roundtrip(dev(img), plan=plan))), bits(want_out))
+    for u8 in (oracle.rand_image_u8(72, 1056, k), inputs.adversarial(32).astype(np.uint8)):
+        want_out, want_coef = oracle.roundtrip(u8, keep=keep, want_coef=True)
+        c16 = torch.empty(u8.shape, dtype=torch.int16, device="cuda")
+        out = dct.roundtrip(dev(u8), coef=c16, plan=plan)
+        assert np.array_equal(host(out), want_out) and np.array_equal(host(c16), want_coef.astype(np.int16))
+        assert np.array_equal(host(dct.roundtrip(dev(u8))), oracle.roundtrip(u8))  # default plan untouched
