@@ -15,11 +15,11 @@ def t(fn):
         for i in range(iters): fn(i)
         e1.record(); torch.cuda.synchronize(); best = min(best, e0.elapsed_time(e1) / iters)
     return best
-for name, dt, paths in (("u8", torch.uint8, (0,)), ("f32", torch.float32, (0, 1))):
+for name, dt, paths in (("u8", torch.uint8, (0, 2)), ("f32", torch.float32, (0, 1))):
     ins = [torch.randint(0, 256, (N, N), device=dev, dtype=torch.int32).to(dt) for _ in range(4)]
     outs = [torch.empty_like(x) for x in ins]
     for path in paths:
         for k in (6, 7, 8, 9, 10, 64):
             plan = m.Plan(keep=m.zigzag_mask(k), path=path)
             ms = t(lambda i: m.roundtrip(ins[i % 4], out=outs[i % 4], plan=plan))
-            print(f"[{tag}] {name} N={N} k={k:2d} {('auto','direct')[path]:6s}->{m.api.last_path():6s} {ms*1e3:8.1f} us  {N*N/ms/1e6:8.1f} Gpx/s", flush=True)
+            print(f"[{tag}] {name} N={N} k={k:2d} {('auto','direct','tma')[path]:6s}->{m.api.last_path():6s} {ms*1e3:8.1f} us  {N*N/ms/1e6:8.1f} Gpx/s", flush=True)

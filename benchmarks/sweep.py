@@ -104,10 +104,12 @@ def main():
             u8 = [x.to(torch.uint8) for x in f32]
             o8 = [torch.empty_like(x) for x in u8]
             add(N, "new/fused u8", time_ms(lambda i: m.roundtrip(u8[i % nb], out=o8[i % nb], plan=plans["default"]), iters), 2, 1, m.api.last_path())
-            del u8, o8
             if N in (2048, 8192):
                 for k in (6, 7, 8, 9, 10):
-                    add(N, f"new/mask k={k} f32", time_ms(lambda i: m.roundtrip(f32[i % nb], out=out[i % nb], plan=plans[f"k{k}"]), iters), 8, 1)
+                    add(N, f"new/mask k={k} f32", time_ms(lambda i: m.roundtrip(f32[i % nb], out=out[i % nb], plan=plans[f"k{k}"]), iters), 8, 1, m.api.last_path())
+                for k in (6, 7, 8, 9, 10):
+                    add(N, f"new/mask k={k} u8", time_ms(lambda i: m.roundtrip(u8[i % nb], out=o8[i % nb], plan=plans[f"k{k}"]), iters), 2, 1, m.api.last_path())
+            del u8, o8
         if have_ref.get("newappr") is not None and N <= 2048:
             # config 1 / README "DCT on CPU (Sequential)": the oracle, one thread, same generator
             try:

@@ -23,7 +23,7 @@ namespace b200dct {
 B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2)
 #undef B200_DECL
 cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_direct_k.cu
-cudaError_t launch_tma_kmask(int k, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
+cudaError_t launch_tma_kmask(int k, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
 
 static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
 {
@@ -445,8 +445,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.run = (uint32_t)tma_max_run;
         const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
-        cudaError_t e = (kmask && pix == DT_F32)
-                            ? launch_tma_kmask(kmask, P, grid, nw * 32, smem, stream, use_pdl() && !capturing)
+        cudaError_t e = kmask
+                            ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing)
                             : launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing);
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
