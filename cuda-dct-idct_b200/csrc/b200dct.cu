@@ -462,6 +462,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     P.shifted = shifted; P.shifted_pitch = in.pitch;
     P.bx = W / 8; P.by = H / 8;
     P.coef_dt = coef_dt;
+    P.zz_smem = (coef_dt == DT_I16ZZ && !partials) ? 1 : 0; // the metrics kernels are launched without dynamic smem
     P.cp = pl->cp;
     dim3 block(32, 4);
     dim3 grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32));

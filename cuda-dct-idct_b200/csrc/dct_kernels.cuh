@@ -86,8 +86,10 @@ struct DirectParams {
     int bx, by;       // blocks per row / block rows
     int coef_dt;      // DT_F32 / DT_I16
     double *partials; // METRICS kernels: 3 doubles per CTA {sum (x-y)^2, sum x^2, non-zero coefficients}
+    int zz_smem;      // 1: the launch carries ZZ_SMEM_BYTES of dynamic shared memory for the zig-zag stream transpose
     CommonParams cp;
 };
+constexpr int ZZ_SMEM_BYTES = 4 * 4096; // one 4 KiB span per warp of the 128-thread CTA
 
 // ---- per-row global accessors (one 8-pixel row of one block) ----
 __device__ __forceinline__ void ld_row_f32(const void *base, float2 (&r)[4])
@@ -128,28 +130,59 @@ __device__ __forceinline__ void unpack_i16(uint4 w, float2 (&r)[4])
     r[0] = make_float2(i16_lo(w.x), i16_hi(w.x)); r[1] = make_float2(i16_lo(w.y), i16_hi(w.y));
     r[2] = make_float2(i16_lo(w.z), i16_hi(w.z)); r[3] = make_float2(i16_lo(w.w), i16_hi(w.w));
 }
-// block <-> 128 contiguous bytes of zig-zag ordered int16 (8 x 128-bit accesses per thread;
-// adjacent lanes are adjacent blocks, so a warp covers one contiguous 4 KiB span)
+// block <-> 128 contiguous bytes of zig-zag ordered int16, as 8 chunks of 16 bytes
+__device__ __forceinline__ uint32_t smem_u32(const void *p);
+__device__ __forceinline__ uint4 lds128u(uint32_t a);
+__device__ __forceinline__ void sts128u(uint32_t a, uint4 v);
+template <int G>
+__device__ __forceinline__ uint4 zigzag_chunk(float2 (&c)[8][4])
+{
+    uint4 w;
+    w.x = pack2_i16(zigzag_elem<8 * G + 0>(c), zigzag_elem<8 * G + 1>(c));
+    w.y = pack2_i16(zigzag_elem<8 * G + 2>(c), zigzag_elem<8 * G + 3>(c));
+    w.z = pack2_i16(zigzag_elem<8 * G + 4>(c), zigzag_elem<8 * G + 5>(c));
+    w.w = pack2_i16(zigzag_elem<8 * G + 6>(c), zigzag_elem<8 * G + 7>(c));
+    return w;
+}
+template <int G>
+__device__ __forceinline__ void zigzag_unchunk(uint4 w, float2 (&c)[8][4])
+{
+    zigzag_elem<8 * G + 0>(c) = i16_lo(w.x); zigzag_elem<8 * G + 1>(c) = i16_hi(w.x);
+    zigzag_elem<8 * G + 2>(c) = i16_lo(w.y); zigzag_elem<8 * G + 3>(c) = i16_hi(w.y);
+    zigzag_elem<8 * G + 4>(c) = i16_lo(w.z); zigzag_elem<8 * G + 5>(c) = i16_hi(w.z);
+    zigzag_elem<8 * G + 6>(c) = i16_lo(w.w); zigzag_elem<8 * G + 7>(c) = i16_hi(w.w);
+}
+// Per-lane access: 8 x 128-bit, lanes 128 bytes apart (every instruction touches 32 half-used
+// sectors).  Used for partial warps at the right edge and when no shared memory was provided.
 __device__ __forceinline__ void st_block_zigzag(void *base, float2 (&c)[8][4])
 {
-    sfor<8>([&](auto g) {
-        uint4 w;
-        w.x = pack2_i16(zigzag_elem<8 * IC(g) + 0>(c), zigzag_elem<8 * IC(g) + 1>(c));
-        w.y = pack2_i16(zigzag_elem<8 * IC(g) + 2>(c), zigzag_elem<8 * IC(g) + 3>(c));
-        w.z = pack2_i16(zigzag_elem<8 * IC(g) + 4>(c), zigzag_elem<8 * IC(g) + 5>(c));
-        w.w = pack2_i16(zigzag_elem<8 * IC(g) + 6>(c), zigzag_elem<8 * IC(g) + 7>(c));
-        reinterpret_cast<uint4 *>(base)[IC(g)] = w;
-    });
+    sfor<8>([&](auto g) { reinterpret_cast<uint4 *>(base)[IC(g)] = zigzag_chunk<IC(g)>(c); });
 }
 __device__ __forceinline__ void ld_block_zigzag(const void *base, float2 (&c)[8][4])
 {
+    sfor<8>([&](auto g) { zigzag_unchunk<IC(g)>(__ldg(reinterpret_cast<const uint4 *>(base) + IC(g)), c); });
+}
+// Cooperative access for a full warp (32 adjacent blocks = one contiguous 4 KiB span): the span
+// is transposed through a 4 KiB shared-memory buffer so that every global instruction moves 512
+// contiguous bytes.  Chunk c of block b lives at b*128 + ((c ^ (b & 7)) * 16): both the per-block
+// side (a quarter-warp = 8 blocks, same c) and the per-span side (a quarter-warp = 8 chunks of
+// one block) hit 8 distinct 16-byte bank groups -- conflict-free.
+__device__ __forceinline__ uint32_t zigzag_slot(int b, int c) { return (uint32_t)(b * 128 + ((c ^ (b & 7)) * 16)); }
+__device__ __forceinline__ void st_warp_zigzag(void *span, uint32_t buf, int lane, float2 (&c)[8][4])
+{
+    sfor<8>([&](auto g) { sts128u(buf + zigzag_slot(lane, IC(g)), zigzag_chunk<IC(g)>(c)); });
+    __syncwarp();
     sfor<8>([&](auto g) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(base) + IC(g));
-        zigzag_elem<8 * IC(g) + 0>(c) = i16_lo(w.x); zigzag_elem<8 * IC(g) + 1>(c) = i16_hi(w.x);
-        zigzag_elem<8 * IC(g) + 2>(c) = i16_lo(w.y); zigzag_elem<8 * IC(g) + 3>(c) = i16_hi(w.y);
-        zigzag_elem<8 * IC(g) + 4>(c) = i16_lo(w.z); zigzag_elem<8 * IC(g) + 5>(c) = i16_hi(w.z);
-        zigzag_elem<8 * IC(g) + 6>(c) = i16_lo(w.w); zigzag_elem<8 * IC(g) + 7>(c) = i16_hi(w.w);
+        reinterpret_cast<uint4 *>(span)[IC(g) * 32 + lane] = lds128u(buf + zigzag_slot(IC(g) * 4 + (lane >> 3), lane & 7));
     });
+}
+__device__ __forceinline__ void ld_warp_zigzag(const void *span, uint32_t buf, int lane, float2 (&c)[8][4])
+{
+    sfor<8>([&](auto g) {
+        sts128u(buf + zigzag_slot(IC(g) * 4 + (lane >> 3), lane & 7), __ldg(reinterpret_cast<const uint4 *>(span) + IC(g) * 32 + lane));
+    });
+    __syncwarp();
+    sfor<8>([&](auto g) { zigzag_unchunk<IC(g)>(lds128u(buf + zigzag_slot(lane, IC(g))), c); });
 }
 __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
 {
@@ -189,6 +222,11 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
+    // zig-zag stream: full warps transpose their 4 KiB span through shared memory (warp-uniform)
+    extern __shared__ uint8_t zz_raw[];
+    const bool zz_coop = P.zz_smem && (int)(blockIdx.y * 32 + 32) <= P.bx;
+    const uint32_t zz_buf = smem_u32(zz_raw) + threadIdx.y * 4096;
+
     float2 p[8][4];
     // ---- load
     if constexpr (MODE == MODE_INV) {
@@ -196,7 +234,9 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         if (P.coef_dt == DT_F32) {
             sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
         } else if (P.coef_dt == DT_I16ZZ) { // pitch = bytes per block-row of the stream
-            ld_block_zigzag((const char *)P.in + (size_t)by * P.in_pitch + (size_t)bxi * 128, p);
+            const char *row = (const char *)P.in + (size_t)by * P.in_pitch;
+            if (zz_coop) ld_warp_zigzag(row + (size_t)blockIdx.y * 4096, zz_buf, threadIdx.x, p);
+            else ld_block_zigzag(row + (size_t)bxi * 128, p);
         } else {
             sfor<8>([&](auto r) {
                 unpack_i16(__ldg(reinterpret_cast<const uint4 *>(src + IC(r) * P.in_pitch + (size_t)bxi * 16)), p[IC(r)]);
@@ -224,7 +264,9 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         if (P.coef_dt == DT_F32) {
             sfor<8>([&](auto r) { st_row_f32(dst + IC(r) * pitch + (size_t)bxi * 32, c[IC(r)]); });
         } else if (P.coef_dt == DT_I16ZZ) {
-            st_block_zigzag((char *)plane + (size_t)by * pitch + (size_t)bxi * 128, c);
+            char *row = (char *)plane + (size_t)by * pitch;
+            if (zz_coop) st_warp_zigzag(row + (size_t)blockIdx.y * 4096, zz_buf, threadIdx.x, c);
+            else st_block_zigzag(row + (size_t)bxi * 128, c);
         } else {
             sfor<8>([&](auto r) {
                 *reinterpret_cast<uint4 *>(dst + IC(r) * pitch + (size_t)bxi * 16) = pack_i16(c[IC(r)]);

@@ -14,6 +14,7 @@ namespace b200dct {
         cfg.gridDim = grid;                                                         \
         cfg.blockDim = block;                                                       \
         cfg.stream = s;                                                             \
+        cfg.dynamicSmemBytes = P.zz_smem ? ZZ_SMEM_BYTES : 0;                       \
         cudaLaunchAttribute attr[1];                                                \
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;            \
         attr[0].val.programmaticStreamSerializationAllowed = 1;                     \

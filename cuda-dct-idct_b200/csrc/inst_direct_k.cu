@@ -13,6 +13,7 @@ static cudaError_t launch_one(const DirectParams &P, dim3 grid, dim3 block, cuda
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.stream = s;
+    cfg.dynamicSmemBytes = P.zz_smem ? ZZ_SMEM_BYTES : 0;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
