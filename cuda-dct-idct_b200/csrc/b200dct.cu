@@ -44,19 +44,31 @@ static cudaError_t launch_tma(bool sparse, int mode, int q, int pix, const TmaPa
 
 using namespace b200dct;
 
-// Sums n CTA partial triples in a fixed order and ADDS the totals into acc[0..2].
-static __global__ void __launch_bounds__(256) k_reduce_partials(const double *__restrict__ partials, size_t n, double *acc)
+// Sums n CTA partial triples in a fixed order and ADDS the totals into acc[0..2].  One CTA (the
+// order of the additions must not depend on scheduling); latency-bound, so every thread issues
+// the loads of 8 strided triples before it adds them.
+constexpr int REDUCE_THREADS = 1024;
+static __global__ void __launch_bounds__(REDUCE_THREADS) k_reduce_partials(const double *__restrict__ partials, size_t n, double *acc)
 {
-    __shared__ double red[3][256];
+    __shared__ double red[3][REDUCE_THREADS];
     double v[3] = {0.0, 0.0, 0.0};
-    for (size_t i = threadIdx.x; i < n; i += 256) {
-        v[0] += partials[i * 3];
-        v[1] += partials[i * 3 + 1];
-        v[2] += partials[i * 3 + 2];
+    size_t i = threadIdx.x;
+    for (; i + 7 * REDUCE_THREADS < n; i += 8 * REDUCE_THREADS) {
+        double t[8][3];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) t[u][q] = partials[(i + (size_t)u * REDUCE_THREADS) * 3 + q];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int q = 0; q < 3; q++) v[q] += t[u][q];
     }
+    for (; i < n; i += REDUCE_THREADS)
+        for (int q = 0; q < 3; q++) v[q] += partials[i * 3 + q];
     for (int q = 0; q < 3; q++) red[q][threadIdx.x] = v[q];
     __syncthreads();
-    for (int s = 128; s > 0; s >>= 1) {
+    for (int s = REDUCE_THREADS / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s)
             for (int q = 0; q < 3; q++) red[q][threadIdx.x] += red[q][threadIdx.x + s];
         __syncthreads();
@@ -66,7 +78,7 @@ static __global__ void __launch_bounds__(256) k_reduce_partials(const double *__
 
 static cudaError_t reduce_partials_sparse(const double *partials, size_t n, double *acc, cudaStream_t s)
 {
-    k_reduce_partials<<<1, 256, 0, s>>>(partials, n, acc);
+    k_reduce_partials<<<1, REDUCE_THREADS, 0, s>>>(partials, n, acc);
     return cudaGetLastError();
 }
 
