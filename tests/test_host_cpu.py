@@ -86,6 +86,12 @@ def test_argument_errors_and_no_cpu_fallback(m):
     assert L.b200dct_roundtrip(p._h, None, 0, 32, addr, 0, 32, None, 0, 0, 8, 8, None) == -1
     assert L.b200dct_roundtrip(p._h, addr, 2, 32, addr, 0, 32, None, 0, 0, 8, 8, None) == -1   # i16 pixels
     assert L.b200dct_roundtrip(p._h, addr, 0, 32, addr, 1, 32, None, 0, 0, 8, 8, None) == -1   # mixed pixel dtypes
+    # zig-zag coefficient stream: coefficient role only, pitch = bytes per block-row (>= (W/8)*128)
+    big = (C.c_float * 256)()
+    baddr = C.addressof(big) + (-C.addressof(big)) % 16
+    assert L.b200dct_roundtrip(p._h, addr, 3, 128, addr, 0, 32, None, 0, 0, 8, 8, None) == -1  # stream as pixels
+    assert L.b200dct_forward(p._h, baddr, 0, 64, baddr, 3, 128, None, 8, 16, None) == -2        # 2 blocks need 256 B
+    assert L.b200dct_forward(p._h, baddr, 0, 64, baddr, 3, 264, None, 8, 16, None) == -3        # pitch not 16 B aligned
     assert L.b200dct_error_string(-4).decode().startswith("no usable CUDA device")
     if not torch.cuda.is_available():
         # valid arguments, no device: the product path refuses -- it never computes on the CPU
