@@ -308,25 +308,39 @@ static int check_plane(const Plane &pl, int W, bool pixels)
 // {next, done} pairs, zero-initialised once; every launch takes the next slot and the kernel
 // leaves its slot zeroed again, so launches on different streams never share a live slot
 // (that would take SCHED_SLOTS launches in flight at once).
+// A launch made under stream capture is replayed many times, possibly while ordinary launches
+// walk the ring, so it gets a pair of its own for good from a second pool (CAPTURE_SLOTS per
+// device, never recycled): replays of one graph exec are stream-ordered by CUDA and every run
+// leaves the pair zeroed.  (Two execs instantiated from the SAME captured graph and replayed
+// concurrently would share a pair -- not supported; B200DCT_TMA_STATIC=1 avoids the counters.)
+// Nothing can be allocated during capture, so both pools are created by the first ordinary call.
 namespace {
 constexpr int SCHED_SLOTS = 4096;
+constexpr int CAPTURE_SLOTS = 4096;
 struct SchedRing {
     uint32_t *base[64] = {};
     unsigned next[64] = {};
+    unsigned next_capture[64] = {};
     std::mutex mu;
 };
 SchedRing g_sched;
 
-uint32_t *sched_slot()
+uint32_t *sched_slot(bool capturing)
 {
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(g_sched.mu);
     if (!g_sched.base[dev]) {
+        if (capturing) return nullptr;
         uint32_t *p = nullptr;
-        if (cudaMalloc(&p, SCHED_SLOTS * 2 * sizeof(uint32_t)) != cudaSuccess) return nullptr;
-        if (cudaMemset(p, 0, SCHED_SLOTS * 2 * sizeof(uint32_t)) != cudaSuccess) { cudaFree(p); return nullptr; }
+        const size_t bytes = (size_t)(SCHED_SLOTS + CAPTURE_SLOTS) * 2 * sizeof(uint32_t);
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return nullptr; }
         g_sched.base[dev] = p;
+    }
+    if (capturing) {
+        if (g_sched.next_capture[dev] >= (unsigned)CAPTURE_SLOTS) return nullptr;
+        return g_sched.base[dev] + 2 * (SCHED_SLOTS + g_sched.next_capture[dev]++);
     }
     const unsigned s = g_sched.next[dev]++ % SCHED_SLOTS;
     return g_sched.base[dev] + 2 * s;
@@ -393,15 +407,28 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // 5120^2 34.9 vs 35.0, 6144^2 48.9 vs 48.0, 8192^2 83.8 vs 81.8.
     const bool big = (unsigned long long)H * (unsigned long long)W >= (28ull << 20);
     const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big);
-    // Under stream capture the launch may later be replayed concurrently with anything, so the
-    // ticket counters cannot be used; the hardware-scheduled direct family (86.9 us at 8192^2)
-    // then beats the TMA family's static split (99.8 us), unless TMA was asked for explicitly.
+    // Under stream capture the launch takes a ticket-counter pair of its own (see SchedRing); when
+    // none is left (or the pools do not exist yet) AUTO falls back to the hardware-scheduled
+    // direct family (86.9 us at 8192^2), which beats the TMA family's static split (99.8 us).
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const bool capturing = cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
-    bool use_tma = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !(capturing && pl->path == B200DCT_PATH_AUTO) &&
-                   !shifted && !partials && get_encode() != nullptr &&
-                   tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
-                   (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
+    static std::once_flag env_once;
+    std::call_once(env_once, [] {
+        const char *e = getenv("B200DCT_TMA_WARPS");
+        if (e && atoi(e) >= 1 && atoi(e) <= 32) tma_warps = atoi(e);
+        const char *r = getenv("B200DCT_TMA_RUN");
+        if (r && atoi(r) >= 1 && atoi(r) <= 4096) tma_max_run = atoi(r);
+        const char *g = getenv("B200DCT_TMA_GRID");
+        if (g && atoi(g) >= 1) tma_grid = atoi(g);
+        const char *d = getenv("B200DCT_TMA_STATIC");
+        if (d && atoi(d) == 1) tma_dynamic = false;
+    });
+    const bool tma_possible = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && !partials && get_encode() != nullptr &&
+                              tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
+                              (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
+    uint32_t *capture_sched = nullptr;
+    if (capturing && tma_dynamic && tma_possible) capture_sched = sched_slot(true);
+    const bool use_tma = tma_possible && !(capturing && !capture_sched && pl->path == B200DCT_PATH_AUTO);
     if (pl->path == B200DCT_PATH_TMA && !use_tma) return B200DCT_ERR_ALIGN;
 
     // retained-coefficient round trips (first k = 6..10 zig-zag coefficients of the default
@@ -412,17 +439,6 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
             if (pl->mask == b200dct_zigzag_mask(k)) kmask = k;
 
     if (use_tma) {
-        static std::once_flag once;
-        std::call_once(once, [] {
-            const char *e = getenv("B200DCT_TMA_WARPS");
-            if (e && atoi(e) >= 1 && atoi(e) <= 32) tma_warps = atoi(e);
-            const char *r = getenv("B200DCT_TMA_RUN");
-            if (r && atoi(r) >= 1 && atoi(r) <= 4096) tma_max_run = atoi(r);
-            const char *g = getenv("B200DCT_TMA_GRID");
-            if (g && atoi(g) >= 1) tma_grid = atoi(g);
-            const char *d = getenv("B200DCT_TMA_STATIC");
-            if (d && atoi(d) == 1) tma_dynamic = false;
-        });
         TmaParams P;
         memset(&P, 0, sizeof(P));
         if (!make_map(&P.in_map, in.ptr, in.dt, in.pitch, H, W) || !make_map(&P.out_map, out.ptr, out.dt, out.pitch, H, W))
@@ -435,8 +451,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.coef_dt = coef_dt;
         P.has_coef = coef.ptr ? 1 : 0;
 
-        // a captured launch may be replayed concurrently with anything: static split there
-        if (tma_dynamic && !capturing) P.sched = sched_slot();
+        // dynamic tickets; a captured launch owns its pair (NULL = static split)
+        if (tma_dynamic) P.sched = capturing ? capture_sched : sched_slot(false);
         P.cp = pl->cp;
         // tile buffers as large as the largest tile image among the planes of this call
         uint32_t buf = tile_bytes_of(in.dt) > tile_bytes_of(out.dt) ? tile_bytes_of(in.dt) : tile_bytes_of(out.dt);

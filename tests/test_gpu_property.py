@@ -92,16 +92,17 @@ def test_concurrent_streams_share_nothing(dct, oracle):
         assert np.array_equal(bits(host(y)), bits(oracle.roundtrip(oracle.rand_image(512, 512, i))))
 
 
-@pytest.mark.parametrize("path,expect", [(0, "direct"), (2, "tma")])
+@pytest.mark.parametrize("path,expect", [(0, "tma"), (1, "direct"), (2, "tma")])
 def test_cuda_graph_capture(dct, oracle, path, expect):
-    """Captured launches never use the ticket counters: AUTO takes the direct family, a forced
-    TMA plan the static tile split; replays stay exact."""
+    """A captured launch owns a ticket-counter pair of its own (left zeroed by every run), so the
+    dynamically scheduled TMA kernels are capturable; replays stay exact, also when ordinary
+    launches run in between."""
     N = 6144                                          # large enough for AUTO to pick TMA outside capture
     img = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float()
     out = torch.empty_like(img)
     plan = dct.Plan(path=path)
     dct.roundtrip(img, out=out, plan=plan)           # warm-up outside capture
-    assert dct.api.last_path() == "tma"
+    assert dct.api.last_path() == expect
     want = out.clone()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -111,10 +112,13 @@ def test_cuda_graph_capture(dct, oracle, path, expect):
         captured_path = dct.api.last_path()
     assert captured_path == expect
     out.zero_()
+    other = torch.empty_like(img)
     for _ in range(3):
         g.replay()
+        dct.roundtrip(img, out=other, plan=plan)      # ordinary launches between replays (ring slots)
     torch.cuda.synchronize()
     assert torch.equal(out.view(torch.int32), want.view(torch.int32))
+    assert torch.equal(other.view(torch.int32), want.view(torch.int32))
     band = host(img[:16])
     assert np.array_equal(bits(host(out[:16])), bits(oracle.roundtrip(band)))
 
