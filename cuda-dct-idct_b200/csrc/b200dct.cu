@@ -364,6 +364,17 @@ static bool use_pdl()
     }
     return v == 1;
 }
+// Under stream capture the attribute becomes a programmatic edge of the graph (CUDA >= 12.3);
+// off unless B200DCT_PDL_CAPTURE=1 (experiment).
+static bool pdl_for(bool capturing)
+{
+    static int cap = -1;
+    if (cap < 0) {
+        const char *p = getenv("B200DCT_PDL_CAPTURE");
+        cap = (p && atoi(p) == 1) ? 1 : 0;
+    }
+    return use_pdl() && (!capturing || cap == 1);
+}
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
 static bool compiled_masks() // env B200DCT_COMPILED_MASKS=0: retained-coefficient masks as runtime data only (A/B)
 {
@@ -474,8 +485,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
         cudaError_t e = kmask
-                            ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing)
-                            : launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, use_pdl() && !capturing);
+                            ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing))
+                            : launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing));
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
         tl_path = "tma";
@@ -508,8 +519,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         tl_path = "direct";
         return B200DCT_OK;
     }
-    if (kmask) e = launch_direct_kmask(kmask, pix, P, grid, block, stream, use_pdl() && !capturing);
-    else e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream, use_pdl() && !capturing);
+    if (kmask) e = launch_direct_kmask(kmask, pix, P, grid, block, stream, pdl_for(capturing));
+    else e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream, pdl_for(capturing));
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "direct";
