@@ -408,10 +408,10 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     const int qm = (!pl->sparse && qmode == Q_IMM) ? Q_PARAM : qmode;
 
     // AUTO: the TMA family wins where the call is HBM-bound (>= 4 bytes moved per pixel: any
-    // f32/i16 plane); all-u8 round trips move 2 B/px, are FP32-pipe bound, and run faster on
-    // the direct family's 16 resident warps per SM (69.7 vs 84 us at 8192^2, round 1).
+    // f32/i16 plane); all-u8 round trips move 2 B/px, are instruction-issue bound, and run faster
+    // on the direct family (64.5 vs 67 us at 8192^2 with the TMA family at 16 warps, round 1).
     const size_t bytes_per_px = elem_size(in.dt) + elem_size(out.dt) + (coef.ptr ? elem_size(coef.dt) : 0);
-    // Dense T (32 FMA/px instead of 22) is FP32-pipe bound as well: direct 98 us vs TMA 105 us.
+    // Dense T (32 FMA/px instead of 22) is issue bound as well: direct 92.5 us vs TMA 112 us.
     // Below ~28 Mpixel the persistent kernel's fixed costs (descriptor fetch, barrier set-up,
     // one CTA per SM) lose to the direct family (C-loop timings with dependent launch,
     // profiles/r01_small_sizes.txt): 256^2 3.4 vs 6.7 us, 2048^2 7.9 vs 9.7, 4096^2 22.9 vs 24.6,
