@@ -156,3 +156,25 @@ def test_image_files_roundtrip_on_host(m, tmp_path):
     m.imageio.save_gray(png, img)
     assert np.array_equal(m.imageio.load_gray(png), img)
     assert m.imageio.crop_to_blocks(img).shape == (32, 48)
+
+
+def test_header_is_plain_c_and_links_from_c(m, tmp_path):
+    """include/b200dct.h compiles as C99 (-pedantic -Werror) and a C program links against
+    libb200dct.so: the boundary carries no C++ or torch types.  On a box without a GPU the
+    program also checks that the host-buffer entry point refuses to run."""
+    import shutil
+    import subprocess
+
+    import torch
+
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(m.lib_path())
+    exe = str(tmp_path / "abi_c99")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "abi_c99.c"), "-o", exe, "-L", libdir, "-lb200dct",
+                           "-Wl,-rpath," + libdir])
+    args = [exe] + (["--device"] if torch.cuda.is_available() else [])
+    out = subprocess.run(args, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "abi_c99 ok" in out.stdout
