@@ -446,3 +446,43 @@ def test_compiled_retained_coefficient_kernels(dct, oracle, k):
         out = dct.roundtrip(dev(u8), coef=c16, plan=plan)
         assert np.array_equal(host(out), want_out) and np.array_equal(host(c16), want_coef.astype(np.int16))
         assert np.array_equal(host(dct.roundtrip(dev(u8))), oracle.roundtrip(u8))  # default plan untouched
+
+
+def test_full_size_masks_and_streams(dct, oracle):
+    """BASELINE sizes (8192^2), size-independent properties of the round-1 additions:
+    a retained-coefficient mask is applied AFTER quantisation, so the masked coefficient plane
+    is the unmasked one with the dropped positions zeroed, on both kernel families and with the
+    mask compiled in (k = 6..10) or as data (k = 5); the zig-zag stream is a permutation of the
+    int16 plane; fused round trip == forward + inverse; bands against the oracle."""
+    N = 8192
+    g = torch.Generator(device="cuda").manual_seed(11)
+    img = torch.randint(0, 256, (N, N), device="cuda", generator=g, dtype=torch.int32).float()
+    full = dct.forward(img)
+    rr, cc = torch.meshgrid(torch.arange(N, device="cuda") % 8, torch.arange(N, device="cuda") % 8, indexing="ij")
+    pos = rr * 8 + cc
+    for k in (5, 6, 10):
+        keep = oracle.zigzag_mask(k)
+        kept = ((torch.tensor(keep, dtype=torch.int64, device="cuda") >> pos) & 1).bool()
+        want = torch.where(kept, full, torch.zeros_like(full))
+        for path in (1, 2):
+            plan = dct.Plan(keep=keep, path=path)
+            coef = torch.empty_like(img)
+            out = dct.roundtrip(img, coef=coef, plan=plan)
+            assert torch.equal(coef, want), (k, path)          # values (0 == -0 here: signs are checked on the bands)
+            assert torch.equal(out.view(torch.int32), dct.inverse(coef, plan=plan).view(torch.int32)), (k, path)
+            for r0 in (0, N - 8):
+                w_out, w_coef = oracle.roundtrip(host(img[r0:r0 + 8]), keep=keep, want_coef=True)
+                assert np.array_equal(bits(host(out[r0:r0 + 8])), bits(w_out)), (k, path, r0)
+                assert np.array_equal(bits(host(coef[r0:r0 + 8])), bits(w_coef)), (k, path, r0)
+        del want, kept
+    # u8 with compiled masks at full size == f32 result through convertToUnsignedChar
+    plan = dct.Plan(keep=oracle.zigzag_mask(10))
+    out8 = dct.roundtrip(img.to(torch.uint8), plan=plan)
+    assert torch.equal(out8, dct.roundtrip(img, plan=plan).clamp(0, 255).to(torch.uint8))
+    # zig-zag stream == permuted int16 plane
+    zz = dct.forward(img, zigzag=True)
+    c16 = dct.forward(img, coef_dtype=torch.int16)
+    blocks = c16.view(N // 8, 8, N // 8, 8).permute(0, 2, 1, 3).reshape(N // 8, N // 8, 64)
+    order = torch.tensor(oracle.zigzag_i16(np.arange(64, dtype=np.float32).reshape(8, 8))[0, 0].astype(np.int64), device="cuda")
+    assert torch.equal(zz, blocks[:, :, order])
+    assert torch.equal(dct.inverse(zz, zigzag=True).view(torch.int32), dct.inverse(full).view(torch.int32))
