@@ -23,6 +23,8 @@ namespace b200dct {
 B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2)
 #undef B200_DECL
 cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_direct_k.cu
+cudaError_t launch_any_f32(bool sparse, int qm, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_any_f32.cu
+cudaError_t launch_any_u8(bool sparse, int qm, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);  // inst_any_u8.cu
 cudaError_t launch_tma_kmask(int k, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
 
 static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
@@ -551,61 +553,42 @@ extern "C" int b200dct_roundtrip(const b200dct_plan *plan, const void *img, b200
 }
 
 // ------------------------------------------------------------------ any size / any alignment
-// Pads by edge replication into an aligned scratch image, or crops back out of it.
-template <class T>
-__global__ void k_pad_edge(const T *__restrict__ src, size_t spitch, int H, int W, T *__restrict__ dst, size_t dpitch,
-                           int Hp, int Wp)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= Wp || y >= Hp) return;
-    const int sx = x < W ? x : W - 1, sy = y < H ? y : H - 1;
-    *((T *)((char *)dst + (size_t)y * dpitch) + x) = *((const T *)((const char *)src + (size_t)sy * spitch) + sx);
-}
-template <class T>
-__global__ void k_crop(const T *__restrict__ src, size_t spitch, T *__restrict__ dst, size_t dpitch, int H, int W)
-{
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= W || y >= H) return;
-    *((T *)((char *)dst + (size_t)y * dpitch) + x) = *((const T *)((const char *)src + (size_t)y * spitch) + x);
-}
-
 extern "C" int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, b200dct_dtype dt, size_t in_pitch,
                                      void *out, size_t out_pitch, int H, int W, void *stream)
 {
+    tl_launches = 0;
     if (!plan || !img || !out || H <= 0 || W <= 0) return B200DCT_ERR_ARG;
     if (dt != B200DCT_F32 && dt != B200DCT_U8) return B200DCT_ERR_ARG;
     const size_t es = elem_size((int)dt);
     if (in_pitch < (size_t)W * es || out_pitch < (size_t)W * es) return B200DCT_ERR_SHAPE;
+    if (((uintptr_t)img % es) || ((uintptr_t)out % es) || (in_pitch % es) || (out_pitch % es)) return B200DCT_ERR_ALIGN;
     const size_t al = dt == B200DCT_U8 ? 8 : 16;
     const bool fast = !(H % 8) && !(W % 8) && !((uintptr_t)img % al) && !((uintptr_t)out % al) && !(in_pitch % al) &&
                       !(out_pitch % al);
     if (fast) return b200dct_roundtrip(plan, img, dt, in_pitch, out, dt, out_pitch, nullptr, B200DCT_F32, 0, H, W, stream);
+    // everything else: one pass of the edge-replicating scalar-access kernel, no scratch image
+    const DevInfo di = dev_info();
+    if (!di.ok) return B200DCT_ERR_NODEVICE;
     cudaStream_t s = (cudaStream_t)stream;
-    const int Hp = (H + 7) & ~7, Wp = (W + 7) & ~7;
-    const size_t pitch = (((size_t)Wp * es) + 255) & ~(size_t)255;
-    char *scratch = nullptr;
-    if (cudaMallocAsync((void **)&scratch, 2 * pitch * (size_t)Hp, s) != cudaSuccess) return B200DCT_ERR_NOMEM;
-    char *pin = scratch, *pout = scratch + pitch * (size_t)Hp;
-    const dim3 blk(256), gp((unsigned)((Wp + 255) / 256), (unsigned)Hp), gc((unsigned)((W + 255) / 256), (unsigned)H);
-    int rc = B200DCT_OK;
-    if (Hp > 65535) rc = B200DCT_ERR_SHAPE; // grid.y limit of the two helper kernels
-    if (rc == B200DCT_OK) {
-        if (dt == B200DCT_F32) k_pad_edge<float><<<gp, blk, 0, s>>>((const float *)img, in_pitch, H, W, (float *)pin, pitch, Hp, Wp);
-        else k_pad_edge<unsigned char><<<gp, blk, 0, s>>>((const unsigned char *)img, in_pitch, H, W, (unsigned char *)pin, pitch, Hp, Wp);
-        rc = b200dct_roundtrip(plan, pin, dt, pitch, pout, dt, pitch, nullptr, B200DCT_F32, 0, Hp, Wp, stream);
-        const int l = tl_launches;
-        if (rc == B200DCT_OK) {
-            if (dt == B200DCT_F32) k_crop<float><<<gc, blk, 0, s>>>((const float *)pout, pitch, (float *)out, out_pitch, H, W);
-            else k_crop<unsigned char><<<gc, blk, 0, s>>>((const unsigned char *)pout, pitch, (unsigned char *)out, out_pitch, H, W);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) rc = (int)e;
-            tl_launches = l + 2;
-        }
-    }
-    cudaFreeAsync(scratch, s);
-    return rc;
+    AnyParams P;
+    memset(&P, 0, sizeof(P));
+    P.in = img; P.in_pitch = in_pitch;
+    P.out = out; P.out_pitch = out_pitch;
+    P.H = H; P.W = W;
+    P.cp = plan->cp;
+    const int qmode = qmode_of(plan);
+    const int qm = (!plan->sparse && qmode == Q_IMM) ? Q_PARAM : qmode;
+    const unsigned nby = (unsigned)((H + 7) / 8), nbx = (unsigned)((W + 7) / 8);
+    dim3 block(32, 4), grid((nby + 3) / 4, (nbx + 31) / 32);
+    if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+    cudaError_t e = dt == B200DCT_F32 ? launch_any_f32(plan->sparse, qm, P, grid, block, s, pdl_for(capturing))
+                                      : launch_any_u8(plan->sparse, qm, P, grid, block, s, pdl_for(capturing));
+    if (e != cudaSuccess) return (int)e;
+    tl_launches = 1;
+    tl_path = "any";
+    return B200DCT_OK;
 }
 
 extern "C" size_t b200dct_metrics_workspace_bytes(int H, int W)

@@ -343,6 +343,88 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     }
 }
 
+// ============================================================== any size, any alignment
+// Fused round trip of an image whose sides need not be multiples of 8 and whose rows need not be
+// aligned (SURVEY.md section 8f "generality"; the reference silently computes garbage there,
+// main_newAppr.cu:261-262): ONE pass, no scratch image.  Blocks that stick out over the right or
+// bottom edge are completed by edge replication (coordinates clamped to the last pixel, the same
+// values np.pad(mode="edge") produces) and only their inside part is stored.
+// Rows are only element-aligned, so accesses are scalar -- but coalesced: a warp owns 8 rows x 256
+// pixels (its 32 blocks), moves every row with 8 instructions of 32 consecutive elements, and
+// re-shapes rows <-> blocks through an 8 KiB shared-memory stage.  In-place calls are safe: a
+// warp reads all of its own region (and nothing else) before it writes it.
+struct AnyParams {
+    const void *in;
+    void *out;
+    size_t in_pitch, out_pitch; // bytes, any value >= W * element size
+    int H, W;
+    CommonParams cp;
+};
+
+template <bool SPARSE, int QMODE, int PIX>
+__global__ void __launch_bounds__(128) k_any(const __grid_constant__ AnyParams P)
+{
+    using elem_t = typename std::conditional<PIX == DT_F32, float, uint8_t>::type;
+    __shared__ __align__(16) uint32_t stage[4][8 * 256];
+    const int lane = threadIdx.x;
+    const long long y0 = ((long long)blockIdx.x * 4 + threadIdx.y) * 8;
+    if (y0 >= P.H) return; // warp-uniform; lanes whose block lies outside the image stay for the row moves
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t *st = stage[threadIdx.y];
+    const int xw = blockIdx.y * 256 + lane;
+
+    // rows -> stage (pixels - 128 as float), coordinates clamped to the image
+    int xs[8];
+    sfor<8>([&](auto s) { xs[IC(s)] = xw + 32 * IC(s) < P.W ? xw + 32 * IC(s) : P.W - 1; });
+    sfor<8>([&](auto r) {
+        const long long y = y0 + IC(r) < P.H ? y0 + IC(r) : P.H - 1;
+        const elem_t *row = reinterpret_cast<const elem_t *>((const char *)P.in + (size_t)y * P.in_pitch);
+        sfor<8>([&](auto s) { st[IC(r) * 256 + 32 * IC(s) + lane] = __float_as_uint((float)row[xs[IC(s)]] - 128.0f); });
+    });
+    __syncwarp();
+    float2 p[8][4];
+    sfor<8>([&](auto r) {
+        const float4 a = *reinterpret_cast<const float4 *>(st + IC(r) * 256 + lane * 8);
+        const float4 b = *reinterpret_cast<const float4 *>(st + IC(r) * 256 + lane * 8 + 4);
+        p[IC(r)][0] = make_float2(a.x, a.y); p[IC(r)][1] = make_float2(a.z, a.w);
+        p[IC(r)][2] = make_float2(b.x, b.y); p[IC(r)][3] = make_float2(b.z, b.w);
+    });
+    __syncwarp(); // every lane has its block: the stage can take the results
+
+    run_block<MODE_RT, SPARSE, QMODE, true>(p, P.cp, [](float2 (&)[8][4]) {});
+
+    // blocks -> stage: the final element value (f32 bits, or the u8 value) per pixel
+    auto fin = [](float v) -> uint32_t {
+        if constexpr (PIX == DT_F32) {
+            return __float_as_uint(v + 128.0f); // add_matrix_scalar, utils_kernels.cu:29
+        } else {
+            uint32_t b;
+            asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(v + 128.0f)); // convertToUnsignedChar, utils.cu:21
+            return b;
+        }
+    };
+    sfor<8>([&](auto r) {
+        *reinterpret_cast<uint4 *>(st + IC(r) * 256 + lane * 8) =
+            make_uint4(fin(p[IC(r)][0].x), fin(p[IC(r)][0].y), fin(p[IC(r)][1].x), fin(p[IC(r)][1].y));
+        *reinterpret_cast<uint4 *>(st + IC(r) * 256 + lane * 8 + 4) =
+            make_uint4(fin(p[IC(r)][2].x), fin(p[IC(r)][2].y), fin(p[IC(r)][3].x), fin(p[IC(r)][3].y));
+    });
+    __syncwarp();
+    sfor<8>([&](auto r) {
+        if (y0 + IC(r) < P.H) {
+            elem_t *row = reinterpret_cast<elem_t *>((char *)P.out + (size_t)(y0 + IC(r)) * P.out_pitch);
+            sfor<8>([&](auto s) {
+                if (xw + 32 * IC(s) < P.W) {
+                    const uint32_t v = st[IC(r) * 256 + 32 * IC(s) + lane];
+                    if constexpr (PIX == DT_F32) row[xw + 32 * IC(s)] = __uint_as_float(v);
+                    else row[xw + 32 * IC(s)] = (uint8_t)v;
+                }
+            });
+        }
+    });
+}
+
 // ============================================================== TMA family
 // Tile = 8 image rows x 32 blocks (256 pixels).  Shared-memory images of a tile:
 //   f32 : 8 KiB, rows of 1 KiB = 8 segments of 128 B, hardware SWIZZLE_128B: the 16-byte

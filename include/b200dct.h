@@ -137,12 +137,12 @@ int b200dct_roundtrip(const b200dct_plan *plan,
                       int H, int W, void *stream);
 
 /* Round trip for ANY image: H and W need not be multiples of 8 and nothing needs to be aligned
- * (SURVEY.md section 8f "generality"; the reference silently computes garbage there,
- * main_newAppr.cu:261-262).  Aligned multiples of 8 go straight to b200dct_roundtrip; anything
- * else is padded to whole blocks by edge replication into a stream-ordered scratch image
- * (cudaMallocAsync), transformed, and cropped back: two small extra kernels and 3x the traffic,
- * but never a wrong answer.  img/out: DEVICE pointers, F32 or U8 (same dtype), H <= 65528 on
- * the padded path. */
+ * beyond the element size (SURVEY.md section 8f "generality"; the reference silently computes
+ * garbage there, main_newAppr.cu:261-262).  Aligned multiples of 8 go straight to
+ * b200dct_roundtrip; anything else runs ONE pass of an edge-aware kernel: blocks that stick out
+ * over the right / bottom edge are completed by edge replication (what np.pad(mode="edge") gives)
+ * and only their inside part is stored -- no scratch image, no extra traffic, never a wrong
+ * answer.  img/out: DEVICE pointers, F32 or U8 (same dtype); out may alias img. */
 int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, b200dct_dtype dt, size_t in_pitch,
                           void *out, size_t out_pitch, int H, int W, void *stream);
 
@@ -201,7 +201,7 @@ int b200dct_selftest_division(float d, unsigned long long first, unsigned long l
 
 /* How many kernels the last call on this thread launched (for bench accounting). */
 int b200dct_last_launch_count(void);
-/* Name of the kernel family the last call on this thread used: "tma" or "direct". */
+/* Name of the kernel family the last call on this thread used: "tma", "direct" or "any". */
 const char *b200dct_last_path(void);
 
 const char *b200dct_error_string(int err);

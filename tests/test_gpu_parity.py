@@ -374,8 +374,9 @@ def test_in_place_calls(dct, oracle, path):
 @pytest.mark.parametrize("shape", [(1, 1), (7, 9), (100, 203), (64, 70), (37, 256), (256, 256), (1081, 1923)])
 @pytest.mark.parametrize("u8", [False, True])
 def test_any_size_round_trip(dct, oracle, shape, u8):
-    """b200dct_roundtrip_any: ragged sizes are padded by edge replication to whole blocks,
-    transformed and cropped; equals the oracle applied to the np.pad(mode='edge') image."""
+    """b200dct_roundtrip_any: ragged sizes run one pass of the edge-replicating kernel (blocks
+    sticking out over the edge are completed by edge replication, only the inside is stored);
+    equals the oracle applied to the np.pad(mode='edge') image, cropped."""
     rng = np.random.default_rng(shape[0] * 1000 + shape[1])
     img = rng.integers(0, 256, shape).astype(np.uint8 if u8 else np.float32)
     H, W = shape
@@ -389,6 +390,22 @@ def test_any_size_round_trip(dct, oracle, shape, u8):
         big[:, 1:W + 1] = dev(img)
         got = host(dct.roundtrip_any(big[:, 1:W + 1]))
         assert np.array_equal(got, want) if u8 else np.array_equal(bits(got), bits(want))
+    # the destination may be a view inside a larger buffer (sentinels survive) or the image itself
+    frame = torch.full((H + 2, W + 5), 77, dtype=torch.uint8 if u8 else torch.float32, device="cuda")
+    d = dev(img)
+    dct.roundtrip_any(d, out=frame[1:H + 1, 2:W + 2])
+    f = host(frame)
+    assert np.array_equal(f[1:H + 1, 2:W + 2], want) if u8 else np.array_equal(bits(f[1:H + 1, 2:W + 2]), bits(want))
+    f[1:H + 1, 2:W + 2] = 77
+    assert (f == 77).all()
+    dct.roundtrip_any(d, out=d)
+    assert np.array_equal(host(d), want) if u8 else np.array_equal(bits(host(d)), bits(want))
+    # plans carry over: retained-coefficient mask and a custom table
+    keep = oracle.zigzag_mask(7)
+    q = (oracle.jpeg_Q() * 0.5 + 3).astype(np.float32)
+    want_p = oracle.roundtrip(np.ascontiguousarray(padded), keep=keep, Q=q)[:H, :W]
+    got_p = host(dct.roundtrip_any(dev(img), plan=dct.Plan(keep=keep, Q=q)))
+    assert np.array_equal(got_p, want_p) if u8 else np.array_equal(bits(got_p), bits(want_p))
 
 
 @pytest.mark.parametrize("u8", [False, True])
