@@ -362,7 +362,7 @@ struct AnyParams {
 };
 
 template <bool SPARSE, int QMODE, int PIX>
-__global__ void __launch_bounds__(128) k_any(const __grid_constant__ AnyParams P)
+__global__ void __launch_bounds__(128, 5) k_any(const __grid_constant__ AnyParams P)
 {
     using elem_t = typename std::conditional<PIX == DT_F32, float, uint8_t>::type;
     __shared__ __align__(16) uint32_t stage[4][8 * 256];
