@@ -262,8 +262,9 @@ def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None, z
 
 
 def roundtrip_any(img, out=None, plan: Plan | None = None, stream=None):
-    """Round trip of a 2-d CUDA tensor of ANY height/width/alignment (ragged edges are padded by
-    edge replication and cropped back; aligned multiples of 8 take the fast path)."""
+    """Round trip of a 2-d CUDA tensor of ANY height/width/alignment: aligned multiples of 8 take
+    the fast path, anything else one pass of the edge-replicating kernel (no scratch image);
+    `out` may be `img` itself or a view inside a larger tensor."""
     import torch
 
     if not (img.is_cuda and img.dim() == 2 and img.stride(1) == 1):
