@@ -53,6 +53,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--gather", action="store_true", help="time the optional NCCL all-gather of the stripes")
+    ap.add_argument("--inverse", default="auto", choices=["auto", "exact"],
+                    help="auto: the library default (factored +-1 LSB inverse for u8 output); exact: the reference's chains")
     ap.add_argument("--fused-gather", action="store_true",
                     help="transform straight into rank 0's image over NVLink peer stores (dist.PeerImage)")
     args = ap.parse_args()
@@ -66,7 +68,14 @@ def main():
     if args.dtype == "f32":
         img = img.float()
     out = torch.empty_like(img)
-    plan = m.Plan()
+    plan = m.Plan(inverse=m.api.INVERSE_EXACT if args.inverse == "exact" else m.api.INVERSE_AUTO)
+    exact = args.dtype == "f32" or args.inverse == "exact"     # else: u8 pixels within 1 LSB of the oracle
+
+    def same(got, ref):
+        if args.dtype == "f32":
+            return np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        return np.array_equal(got, ref) if exact else int(np.abs(got.astype(np.int16) - ref.astype(np.int16)).max()) <= 1
+
     for _ in range(args.warmup):
         m.roundtrip(img, out=out, plan=plan)
     torch.cuda.synchronize()
@@ -89,7 +98,7 @@ def main():
         band = inputs.splitmix_u8(16 * W, 42, (r0 + a) * W).reshape(16, W)
         ref = o.roundtrip(band if args.dtype == "u8" else band.astype(np.float32))
         got = out[a:a + 16].cpu().numpy()
-        ok = ok and (np.array_equal(got, ref) if args.dtype == "u8" else np.array_equal(got.view(np.uint32), ref.view(np.uint32)))
+        ok = ok and same(got, ref)
     ok_all = m.dist.sum_over_ranks(0.0 if ok else 1.0, dev) == 0.0
 
     gather_ms = None
@@ -130,17 +139,17 @@ def main():
                     band = inputs.splitmix_u8(16 * W, 42, b0 * W).reshape(16, W)
                     ref = o.roundtrip(band if args.dtype == "u8" else band.astype(np.float32))
                     got = full[b0:b0 + 16].cpu().numpy()
-                    fused_ok = fused_ok and (np.array_equal(got, ref) if args.dtype == "u8"
-                                             else np.array_equal(got.view(np.uint32), ref.view(np.uint32)))
+                    fused_ok = fused_ok and same(got, ref)
         m.dist.barrier()
     es = 1 if args.dtype == "u8" else 4
     if rank == 0:
         print(json.dumps({
             "workload": f"{H}x{W} {args.dtype} image striped by block-rows over {world} GPU(s) (= {H * W // (8192 * 8192)} images of 8192^2)",
             "n_gpus": world, "ms_per_step": ms, "gpixel_s": H * W / ms / 1e6, "gb_s_per_gpu": 2 * es * H * W / world / ms / 1e6,
-            "rows_per_gpu": r1 - r0, "kernel_path": m.api.last_path(), "parity_vs_oracle_bit_exact": bool(ok_all),
+            "rows_per_gpu": r1 - r0, "kernel_path": m.api.last_path(), "parity_vs_oracle": bool(ok_all),
+            "parity_criterion": "bit-exact" if exact else "u8 within 1 LSB (factored inverse, the library default for 8-bit output)",
             "optional_gather_ms": gather_ms, "fused_transform_plus_gather_ms": fused_ms,
-            "fused_gather_parity_bit_exact": fused_ok, "steps": args.steps, "collective_on_data_path": "none"}))
+            "fused_gather_parity": fused_ok, "steps": args.steps, "collective_on_data_path": "none"}))
     m.dist.barrier()
     m.dist.shutdown()
 

@@ -18,6 +18,8 @@ ALL_COEFFS = (1 << 64) - 1
 
 F32, U8, I16, I16_ZIGZAG = 0, 1, 2, 3
 PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
+INVERSE_AUTO, INVERSE_EXACT, INVERSE_FACTORED = 0, 1, 2
+DENSE_AUTO, DENSE_CHAIN, DENSE_SYMMETRIC = 0, 1, 2
 
 
 class B200DCTError(RuntimeError):
@@ -56,6 +58,9 @@ def lib() -> C.CDLL:
         L.b200dct_zigzag_mask.restype = u64
         L.b200dct_plan_set_path.argtypes = [vp, i]
         L.b200dct_plan_is_sparse.argtypes = [vp]
+        L.b200dct_plan_set_inverse.argtypes = [vp, i]
+        L.b200dct_plan_set_dense.argtypes = [vp, i]
+        L.b200dct_plan_kernel_kind.argtypes = [vp]
         L.b200dct_forward.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, i, vp]
         L.b200dct_inverse.argtypes = [vp, vp, i, sz, vp, i, sz, i, i, vp]
         L.b200dct_roundtrip.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp]
@@ -110,7 +115,8 @@ def _f64(a) -> "C.Array":
 class Plan:
     """T, Q and the retained-coefficient mask (b200dct_plan)."""
 
-    def __init__(self, T=None, Q=None, keep: int = ALL_COEFFS, path: int = PATH_AUTO):
+    def __init__(self, T=None, Q=None, keep: int = ALL_COEFFS, path: int = PATH_AUTO, inverse: int = INVERSE_AUTO,
+                 dense: int = DENSE_AUTO):
         self._h = C.c_void_p()
         _check(lib().b200dct_plan_create(C.byref(self._h)))
         if T is not None:
@@ -121,6 +127,10 @@ class Plan:
             self.set_keep_mask(keep)
         if path != PATH_AUTO:
             self.set_path(path)
+        if inverse != INVERSE_AUTO:
+            self.set_inverse(inverse)
+        if dense != DENSE_AUTO:
+            self.set_dense(dense)
 
     def set_transform(self, T) -> None:
         _check(lib().b200dct_plan_set_transform(self._h, _f64(T)))
@@ -138,6 +148,21 @@ class Plan:
 
     def set_path(self, path: int) -> None:
         _check(lib().b200dct_plan_set_path(self._h, path))
+
+    def set_inverse(self, mode: int) -> None:
+        """INVERSE_EXACT: the reference's FMA chains everywhere (u8 pixels bit-identical to the
+        reference); INVERSE_AUTO / INVERSE_FACTORED: butterfly inverse for 8-bit output (+-1 LSB)."""
+        _check(lib().b200dct_plan_set_inverse(self._h, mode))
+
+    def set_dense(self, mode: int) -> None:
+        """DENSE_CHAIN: ordered FMA chains for a dense T (bit-identical to the oracle with that T);
+        DENSE_AUTO / DENSE_SYMMETRIC: even/odd evaluation when T has the DCT-II symmetry."""
+        _check(lib().b200dct_plan_set_dense(self._h, mode))
+
+    @property
+    def kernel_kind(self) -> int:
+        """0 ordered chains (dense T), 1 Haweel sparse kernels, 2 symmetric dense kernels."""
+        return int(lib().b200dct_plan_kernel_kind(self._h))
 
     @property
     def is_sparse(self) -> bool:

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -17,30 +18,33 @@
 namespace b200dct {
 // one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
 #define B200_DECL(tag)                                                                                                  \
-    cudaError_t launch_direct_##tag(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);     \
-    cudaError_t launch_direct_metrics_##tag(int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);      \
-    cudaError_t launch_tma_##tag(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);
-B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2)
+    cudaError_t launch_direct_##tag(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);     \
+    cudaError_t launch_direct_metrics_##tag(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);      \
+    cudaError_t launch_tma_##tag(int mode, int pix, bool finv, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);
+B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2) B200_DECL(y1) B200_DECL(y2)
 #undef B200_DECL
 cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_direct_k.cu
-cudaError_t launch_any_f32(bool sparse, int qm, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_any_f32.cu
-cudaError_t launch_any_u8(bool sparse, int qm, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);  // inst_any_u8.cu
+cudaError_t launch_any_f32(int tk, int qm, bool finv, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_any_f32.cu
+cudaError_t launch_any_u8(int tk, int qm, bool finv, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);  // inst_any_u8.cu
 cudaError_t launch_tma_kmask(int k, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
 
-static cudaError_t launch_direct(bool sparse, int mode, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
+static cudaError_t launch_direct(int tk, int mode, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
 {
-    if (sparse) return q == 0 ? launch_direct_s0(mode, pix, P, g, b, s, pdl) : q == 1 ? launch_direct_s1(mode, pix, P, g, b, s, pdl) : launch_direct_s2(mode, pix, P, g, b, s, pdl);
-    return q == 1 ? launch_direct_d1(mode, pix, P, g, b, s, pdl) : launch_direct_d2(mode, pix, P, g, b, s, pdl);
+    if (tk == TK_DENSE_SYM) return q == 1 ? launch_direct_y1(mode, pix, finv, P, g, b, s, pdl) : launch_direct_y2(mode, pix, finv, P, g, b, s, pdl);
+    if (tk == TK_HAWEEL) return q == 0 ? launch_direct_s0(mode, pix, finv, P, g, b, s, pdl) : q == 1 ? launch_direct_s1(mode, pix, finv, P, g, b, s, pdl) : launch_direct_s2(mode, pix, finv, P, g, b, s, pdl);
+    return q == 1 ? launch_direct_d1(mode, pix, finv, P, g, b, s, pdl) : launch_direct_d2(mode, pix, finv, P, g, b, s, pdl);
 }
-static cudaError_t launch_direct_metrics(bool sparse, int q, int pix, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
+static cudaError_t launch_direct_metrics(int tk, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
 {
-    if (sparse) return q == 0 ? launch_direct_metrics_s0(pix, P, g, b, s) : q == 1 ? launch_direct_metrics_s1(pix, P, g, b, s) : launch_direct_metrics_s2(pix, P, g, b, s);
-    return q == 1 ? launch_direct_metrics_d1(pix, P, g, b, s) : launch_direct_metrics_d2(pix, P, g, b, s);
+    if (tk == TK_DENSE_SYM) return q == 1 ? launch_direct_metrics_y1(pix, finv, P, g, b, s) : launch_direct_metrics_y2(pix, finv, P, g, b, s);
+    if (tk == TK_HAWEEL) return q == 0 ? launch_direct_metrics_s0(pix, finv, P, g, b, s) : q == 1 ? launch_direct_metrics_s1(pix, finv, P, g, b, s) : launch_direct_metrics_s2(pix, finv, P, g, b, s);
+    return q == 1 ? launch_direct_metrics_d1(pix, finv, P, g, b, s) : launch_direct_metrics_d2(pix, finv, P, g, b, s);
 }
-static cudaError_t launch_tma(bool sparse, int mode, int q, int pix, const TmaParams &P, int g, int b, size_t smem, cudaStream_t s, bool pdl)
+static cudaError_t launch_tma(int tk, int mode, int q, int pix, bool finv, const TmaParams &P, int g, int b, size_t smem, cudaStream_t s, bool pdl)
 {
-    if (sparse) return q == 0 ? launch_tma_s0(mode, pix, P, g, b, smem, s, pdl) : q == 1 ? launch_tma_s1(mode, pix, P, g, b, smem, s, pdl) : launch_tma_s2(mode, pix, P, g, b, smem, s, pdl);
-    return q == 1 ? launch_tma_d1(mode, pix, P, g, b, smem, s, pdl) : launch_tma_d2(mode, pix, P, g, b, smem, s, pdl);
+    if (tk == TK_DENSE_SYM) return q == 1 ? launch_tma_y1(mode, pix, finv, P, g, b, smem, s, pdl) : launch_tma_y2(mode, pix, finv, P, g, b, smem, s, pdl);
+    if (tk == TK_HAWEEL) return q == 0 ? launch_tma_s0(mode, pix, finv, P, g, b, smem, s, pdl) : q == 1 ? launch_tma_s1(mode, pix, finv, P, g, b, smem, s, pdl) : launch_tma_s2(mode, pix, finv, P, g, b, smem, s, pdl);
+    return q == 1 ? launch_tma_d1(mode, pix, finv, P, g, b, smem, s, pdl) : launch_tma_d2(mode, pix, finv, P, g, b, smem, s, pdl);
 }
 } // namespace b200dct
 
@@ -92,6 +96,10 @@ struct b200dct_plan {
     bool q_default;  // Q is the JPEG luminance table
     bool q_fastdiv;  // every divisor is in the exhaustively proven set (integers 1..255)
     int path;        // b200dct_path
+    int inverse;     // b200dct_inverse_mode
+    int dense;       // b200dct_dense_mode
+    bool symmetric;  // dense T whose even rows are symmetric and odd rows antisymmetric
+    int tk;          // TK_HAWEEL / TK_DENSE_SYM / TK_DENSE: the kernels this plan runs
     CommonParams cp; // device-ready tables
 };
 
@@ -116,6 +124,18 @@ static void plan_refresh(b200dct_plan *pl)
         pl->cp.t.t[k] = pl->T[k];
         pl->cp.t.tt[(k % 8) * 8 + k / 8] = pl->T[k];
     }
+    // even rows symmetric, odd rows antisymmetric (exact float comparison): the true DCT-II and
+    // every matrix of that family -- evaluated through its even/odd halves unless the plan asks
+    // for the ordered chains
+    pl->symmetric = true;
+    for (int r = 0; r < 8; r++)
+        for (int n = 0; n < 4; n++) {
+            const float a = pl->T[r * 8 + n], b = pl->T[r * 8 + 7 - n];
+            if (!isfinite(a) || ((r & 1) ? (a != -b) : (a != b))) pl->symmetric = false;
+        }
+    for (int i = 0; i < 4; i++)
+        for (int n = 0; n < 4; n++) pl->cp.t.eo[i * 4 + n] = make_float2(pl->T[(2 * i) * 8 + n], pl->T[(2 * i + 1) * 8 + n]);
+    pl->tk = pl->sparse ? TK_HAWEEL : ((pl->symmetric && pl->dense != B200DCT_DENSE_CHAIN) ? TK_DENSE_SYM : TK_DENSE);
 }
 
 static int qmode_of(const b200dct_plan *pl)
@@ -136,6 +156,19 @@ extern "C" int b200dct_plan_create(b200dct_plan **out)
     }
     pl->mask = ~(uint64_t)0;
     pl->path = B200DCT_PATH_AUTO;
+    // env B200DCT_DENSE=chain|symmetric|auto: default dense-T arithmetic of new plans
+    pl->dense = B200DCT_DENSE_AUTO;
+    if (const char *e = getenv("B200DCT_DENSE")) {
+        if (!strcmp(e, "chain")) pl->dense = B200DCT_DENSE_CHAIN;
+        else if (!strcmp(e, "symmetric")) pl->dense = B200DCT_DENSE_SYMMETRIC;
+    }
+    // env B200DCT_INVERSE=exact|factored|auto: default inverse mode of new plans (a caller that wants
+    // the reference's u8 bits everywhere, e.g. through the compat library, sets "exact")
+    pl->inverse = B200DCT_INVERSE_AUTO;
+    if (const char *e = getenv("B200DCT_INVERSE")) {
+        if (!strcmp(e, "exact")) pl->inverse = B200DCT_INVERSE_EXACT;
+        else if (!strcmp(e, "factored")) pl->inverse = B200DCT_INVERSE_FACTORED;
+    }
     plan_refresh(pl);
     *out = pl;
     return B200DCT_OK;
@@ -203,6 +236,29 @@ extern "C" int b200dct_plan_set_path(b200dct_plan *pl, b200dct_path path)
     if (!pl || path < B200DCT_PATH_AUTO || path > B200DCT_PATH_TMA) return B200DCT_ERR_ARG;
     pl->path = path;
     return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_set_inverse(b200dct_plan *pl, b200dct_inverse_mode mode)
+{
+    if (!pl || mode < B200DCT_INVERSE_AUTO || mode > B200DCT_INVERSE_FACTORED) return B200DCT_ERR_ARG;
+    pl->inverse = mode;
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_set_dense(b200dct_plan *pl, b200dct_dense_mode mode)
+{
+    if (!pl || mode < B200DCT_DENSE_AUTO || mode > B200DCT_DENSE_SYMMETRIC) return B200DCT_ERR_ARG;
+    pl->dense = mode;
+    plan_refresh(pl);
+    return B200DCT_OK;
+}
+// 0 ordered chains, 1 Haweel's sparse kernels, 2 symmetric dense kernels
+extern "C" int b200dct_plan_kernel_kind(const b200dct_plan *pl) { return pl ? pl->tk : B200DCT_ERR_ARG; }
+
+// The factored inverse applies to 8-bit pixel output of Haweel's T (contract: +-1 LSB).
+static bool use_factored_inverse(const b200dct_plan *pl, int mode, int pix)
+{
+    return pl->sparse && pix == DT_U8 && mode != MODE_FWD && pl->inverse != B200DCT_INVERSE_EXACT;
 }
 
 extern "C" int b200dct_plan_is_sparse(const b200dct_plan *pl) { return pl ? (pl->sparse ? 1 : 0) : B200DCT_ERR_ARG; }
@@ -451,6 +507,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         for (int k = 6; k <= 10; k++)
             if (pl->mask == b200dct_zigzag_mask(k)) kmask = k;
 
+    const bool finv = !(kmask && !partials) && use_factored_inverse(pl, mode, pix); // compile-time-mask kernels keep the chains
     if (use_tma) {
         TmaParams P;
         memset(&P, 0, sizeof(P));
@@ -473,7 +530,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.buf_bytes = buf;
         // warps per CTA: the flavour's CTA size (8 for sparse-T f32; all the CTA holds for the
         // FP32-bound u8 and dense-T flavours), limited by 227 KiB of shared memory
-        const int max_w = tma_cta_threads(pix, pl->sparse) / 32;
+        const int max_w = tma_cta_threads(pix, pl->tk) / 32;
         int nw = tma_warps > 0 ? tma_warps : (pix == DT_U8 || !pl->sparse ? max_w : B200DCT_TMA_DEFAULT_WARPS);
         if (nw > max_w) nw = max_w;
         const int smem_w = (int)((227u * 1024u - 1024u) / (2u * buf + 8u));
@@ -488,7 +545,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
         cudaError_t e = kmask
                             ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing))
-                            : launch_tma(pl->sparse, mode, qm, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing));
+                            : launch_tma(pl->tk, mode, qm, pix, finv, P, grid, nw * 32, smem, stream, pdl_for(capturing));
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
         tl_path = "tma";
@@ -513,7 +570,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         // fused metrics: per-CTA partials, then one fixed-order reduction into acc[0..2]
         if (mode != MODE_RT || in.ptr == out.ptr) return B200DCT_ERR_ARG;
         P.partials = partials;
-        e = launch_direct_metrics(pl->sparse, qm, pix, P, grid, block, stream);
+        e = launch_direct_metrics(pl->tk, qm, pix, finv, P, grid, block, stream);
         if (e != cudaSuccess) return (int)e;
         e = reduce_partials_sparse(partials, (size_t)grid.x * grid.y, acc, stream);
         if (e != cudaSuccess) return (int)e;
@@ -522,7 +579,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         return B200DCT_OK;
     }
     if (kmask) e = launch_direct_kmask(kmask, pix, P, grid, block, stream, pdl_for(capturing));
-    else e = launch_direct(pl->sparse, mode, qm, pix, P, grid, block, stream, pdl_for(capturing));
+    else e = launch_direct(pl->tk, mode, qm, pix, finv, P, grid, block, stream, pdl_for(capturing));
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "direct";
@@ -583,8 +640,9 @@ extern "C" int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, 
     if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
-    cudaError_t e = dt == B200DCT_F32 ? launch_any_f32(plan->sparse, qm, P, grid, block, s, pdl_for(capturing))
-                                      : launch_any_u8(plan->sparse, qm, P, grid, block, s, pdl_for(capturing));
+    const bool finv = use_factored_inverse(plan, MODE_RT, (int)dt);
+    cudaError_t e = dt == B200DCT_F32 ? launch_any_f32(plan->tk, qm, false, P, grid, block, s, pdl_for(capturing))
+                                      : launch_any_u8(plan->tk, qm, finv, P, grid, block, s, pdl_for(capturing));
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "any";

@@ -63,6 +63,22 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
     return *reinterpret_cast<float2 *>(&rd);
 }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b)
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
 __device__ __forceinline__ float2 bc(float v) { return make_float2(v, v); }
 
 // ---------------------------------------------------------------- constants
@@ -110,6 +126,10 @@ struct QuantTables {
 struct DenseT {
     float t[64];  // T[r][c]
     float tt[64]; // T^T, so that {T[x][i],T[x+1][i]} is one aligned 8-byte constant
+    // symmetric kernels (rows 2i symmetric, rows 2i+1 antisymmetric, e.g. the true DCT-II):
+    // eo[i*4+n] = {T[2i][n], T[2i+1][n]} for n < 4 -- the halves of a packed instruction are an
+    // even (symmetric) and an odd (antisymmetric) basis function
+    float2 eo[16];
 };
 
 // ---------------------------------------------------------------- transform policies
@@ -165,9 +185,9 @@ struct RuntimeT {
 // 82.5 us) but 1.3 % faster over 4000 power-capped launches (83.7 -> 82.6 us: fewer instructions,
 // less power, same clocks), which is the regime that counts.  All kernels use it; the policy
 // stays a template parameter (HaweelT<INV, CBANK>).
-static __constant__ float2 c_pairs[5] = {{(float)0.35355339, -(float)0.35355339}, {(float)0.5, -(float)0.5},
+static __constant__ float2 c_pairs[6] = {{(float)0.35355339, -(float)0.35355339}, {(float)0.5, -(float)0.5},
                                   {(float)0.4472136, (float)0.2236068}, {(float)0.2236068, -(float)0.4472136},
-                                  {(float)0.70710678, -(float)0.70710678}};
+                                  {(float)0.70710678, -(float)0.70710678}, {1.0f, -1.0f}};
 __host__ __device__ constexpr int pair_index(float na, float nb)
 {
     return (na == (float)0.35355339) ? 0 : (na == (float)0.5) ? 1 : (na == (float)0.4472136) ? 2
@@ -370,6 +390,145 @@ __device__ __forceinline__ void inverse_block(float2 (&p)[8][4], const TI &ti, c
         });
         row_pass<TI, ZeroCols<KM>, NeedAll>(m, o, ti);
         sfor<4>([&](auto j) { p[IC(y)][IC(j)] = make_float2(o[2 * IC(j)], o[2 * IC(j) + 1]); });
+    });
+}
+
+// ---------------------------------------------------------------- factored inverse (+-1 LSB)
+// Haweel's T has symmetric even rows (0,2,4,6) and antisymmetric odd rows (1,3,5,7), so the
+// 8-point inverse x[n] = sum_k T[k][n] c[k] splits into x[n] = E[n] + O[n], x[7-n] = E[n] - O[n]:
+//     u = a c0 (+bias)   A = u + a c4   B = u - a c4     P = p c2 + q c6   R = q c2 - p c6
+//     E0 = A + P   E3 = A - P   E1 = B + R   E2 = B - R
+//     x0,x7 = E0 +- h (c1 + c5)   x1,x6 = E1 +- h (c1 - c5)   x2,x5 = E2 -+ s c3   x3,x4 = E3 -+ s c7
+// 21 operations instead of the 44 ordered FMAs of the reference chain (cuda_matrix_idct,
+// main_newAppr.cu:236-239,246-248).  The sums are re-associated, so the float result differs
+// from the chain in the last bits (|diff| <~ 1e-4 at pixel scale): used only where the contract
+// is "+-1 LSB" (8-bit pixel output, SURVEY.md section 7.2 "inverse pass has slack"), never for the
+// forward transform (quantised coefficients stay bit-exact) and never for f32 pixels.
+// Column pass: two adjacent columns per packed instruction, constants broadcast immediates.
+// Row pass: the two halves of a packed instruction are the two members of a butterfly, the
+// input is a broadcast register and the constant pair {k,-k} comes from the constant bank.
+// The +128 of add_matrix_scalar (utils_kernels.cu:29) rides on the DC term of the row pass
+// (every output contains u exactly once), so it costs nothing.
+template <bool BIAS128, class QP>
+__device__ __forceinline__ void inverse_block_fast(float2 (&p)[8][4], const QP &qp)
+{
+    constexpr float a = (float)0.35355339, h = (float)0.5, pp = (float)0.4472136, q = (float)0.2236068,
+                    s = (float)0.70710678;
+    sfor<8>([&](auto y) {
+        sfor<4>([&](auto j) {
+            p[IC(y)][IC(j)].x *= qp.d(IC(y) * 8 + 2 * IC(j)); // multiply_matrices, utils_kernels.cu:55
+            p[IC(y)][IC(j)].y *= qp.d(IC(y) * 8 + 2 * IC(j) + 1);
+        });
+    });
+    sfor<4>([&](auto j) {
+        const float2 c0 = p[0][IC(j)], c1 = p[1][IC(j)], c2 = p[2][IC(j)], c3 = p[3][IC(j)], c4 = p[4][IC(j)],
+                     c5 = p[5][IC(j)], c6 = p[6][IC(j)], c7 = p[7][IC(j)];
+        const float2 u = fmul2(c0, bc(a));
+        const float2 A = ffma2(c4, bc(a), u), B = ffma2(c4, bc(-a), u);
+        const float2 P = ffma2(c6, bc(q), fmul2(c2, bc(pp))), R = ffma2(c6, bc(-pp), fmul2(c2, bc(q)));
+        const float2 E0 = fadd2(A, P), E3 = fsub2(A, P), E1 = fadd2(B, R), E2 = fsub2(B, R);
+        const float2 sm = fadd2(c1, c5), df = fsub2(c1, c5);
+        p[0][IC(j)] = ffma2(sm, bc(h), E0); p[7][IC(j)] = ffma2(sm, bc(-h), E0);
+        p[1][IC(j)] = ffma2(df, bc(h), E1); p[6][IC(j)] = ffma2(df, bc(-h), E1);
+        p[2][IC(j)] = ffma2(c3, bc(-s), E2); p[5][IC(j)] = ffma2(c3, bc(s), E2);
+        p[3][IC(j)] = ffma2(c7, bc(-s), E3); p[4][IC(j)] = ffma2(c7, bc(s), E3);
+    });
+    sfor<8>([&](auto y) {
+        const float m0 = p[IC(y)][0].x, m1 = p[IC(y)][0].y, m2 = p[IC(y)][1].x, m3 = p[IC(y)][1].y,
+                    m4 = p[IC(y)][2].x, m5 = p[IC(y)][2].y, m6 = p[IC(y)][3].x, m7 = p[IC(y)][3].y;
+        const float u = BIAS128 ? __fmaf_rn(m0, a, 128.0f) : m0 * a;
+        const float2 AB = ffma2(bc(m4), pair_constant<0>(), bc(u));                       // {A, B}
+        const float2 PR = ffma2(bc(m6), pair_constant<3>(), fmul2(bc(m2), pair_constant<2>())); // {P, R}
+        const float2 SD = ffma2(bc(m5), pair_constant<5>(), bc(m1));                      // {c1+c5, c1-c5}
+        const float2 E03 = ffma2(bc(PR.x), pair_constant<5>(), bc(AB.x));                 // {E0, E3}
+        const float2 E12 = ffma2(bc(PR.y), pair_constant<5>(), bc(AB.y));                 // {E1, E2}
+        const float2 x07 = ffma2(bc(SD.x), pair_constant<1>(), bc(E03.x));
+        const float2 x16 = ffma2(bc(SD.y), pair_constant<1>(), bc(E12.x));
+        const float2 x25 = ffma2(bc(-m3), pair_constant<4>(), bc(E12.y));
+        const float2 x34 = ffma2(bc(-m7), pair_constant<4>(), bc(E03.y));
+        p[IC(y)][0] = make_float2(x07.x, x16.x); p[IC(y)][1] = make_float2(x25.x, x34.x);
+        p[IC(y)][2] = make_float2(x34.y, x25.y); p[IC(y)][3] = make_float2(x16.y, x07.y);
+    });
+}
+
+// ---------------------------------------------------------------- dense T with even/odd symmetry
+// A dense T whose even rows are symmetric (T[k][n] == T[k][7-n]) and whose odd rows are
+// antisymmetric (the true DCT-II, and every "exact" matrix the cuBLAS variants of the reference are
+// meant for) needs only half the products:
+//   forward  y[k] = sum_{n<4} T[k][n] (x[n] +- x[7-n])            8 add/sub + 32 FMA instead of 64 FMA
+//   inverse  x[n], x[7-n] = E[n] +- O[n],  E/O[n] = sum_{k even/odd} T[k][n] c[k]   32 FMA + 8 add/sub
+// The sums are re-associated with respect to the reference's cuBLAS calls (main_cublass.cu:234-241,
+// main_cublass_2.cu:228-235) -- but so is cuBLAS itself with respect to any fixed chain (its
+// accumulation order is undocumented; measured 8-54 of 65536 quantised coefficients differ from the
+// ascending FMA chain), so the criterion for dense T is a mismatch COUNT against the
+// live cuBLAS reference, pixels within 1 LSB.  Plans select it automatically when T has the
+// structure (b200dct_dense_mode); any other dense T runs the ordered chains.
+// Column passes: two adjacent columns per packed instruction, T entries broadcast from the
+// parameter bank.  Row passes: the two halves are an (even, odd) pair: {s_n, d_n} = {m[n]+m[7-n],
+// m[n]-m[7-n]} feeds {y[2i], y[2i+1]} and {c[2i], c[2i+1]} feeds {E_n, O_n}, so inputs and outputs
+// are exactly the natural column pairs p[row][j] -- no re-pairing moves.
+template <class QP>
+__device__ __forceinline__ void forward_block_sym(float2 (&p)[8][4], const DenseT &m, const QP &qp)
+{
+    sfor<4>([&](auto j) {
+        float2 sd[8]; // [n] = x[n] + x[7-n], [4+n] = x[n] - x[7-n]
+        sfor<4>([&](auto n) {
+            sd[IC(n)] = fadd2(p[IC(n)][IC(j)], p[7 - IC(n)][IC(j)]);
+            sd[4 + IC(n)] = fsub2(p[IC(n)][IC(j)], p[7 - IC(n)][IC(j)]);
+        });
+        sfor<8>([&](auto k) {
+            constexpr int base = (IC(k) & 1) * 4;
+            float2 acc = fmul2(sd[base], bc(m.t[IC(k) * 8]));
+            sfor<3>([&](auto n) { acc = ffma2(sd[base + 1 + IC(n)], bc(m.t[IC(k) * 8 + 1 + IC(n)]), acc); });
+            p[IC(k)][IC(j)] = acc;
+        });
+    });
+    sfor<8>([&](auto y) {
+        const float r[8] = {p[IC(y)][0].x, p[IC(y)][0].y, p[IC(y)][1].x, p[IC(y)][1].y,
+                            p[IC(y)][2].x, p[IC(y)][2].y, p[IC(y)][3].x, p[IC(y)][3].y};
+        float2 sd[4];
+        sfor<4>([&](auto n) { sd[IC(n)] = ffma2(bc(r[7 - IC(n)]), pair_constant<5>(), bc(r[IC(n)])); });
+        sfor<4>([&](auto i) {
+            float2 acc = fmul2(sd[0], m.eo[IC(i) * 4]);
+            sfor<3>([&](auto n) { acc = ffma2(sd[1 + IC(n)], m.eo[IC(i) * 4 + 1 + IC(n)], acc); });
+            p[IC(y)][IC(i)].x = quantise(acc.x, IC(y) * 8 + 2 * IC(i), qp);
+            p[IC(y)][IC(i)].y = quantise(acc.y, IC(y) * 8 + 2 * IC(i) + 1, qp);
+        });
+    });
+}
+
+// C -> pixels WITH the +128 (it rides on the first product of every E_n in the row pass).
+template <class QP>
+__device__ __forceinline__ void inverse_block_sym(float2 (&p)[8][4], const DenseT &m, const QP &qp)
+{
+    sfor<8>([&](auto y) {
+        sfor<4>([&](auto j) {
+            p[IC(y)][IC(j)].x *= qp.d(IC(y) * 8 + 2 * IC(j)); // multiply_matrices, utils_kernels.cu:55
+            p[IC(y)][IC(j)].y *= qp.d(IC(y) * 8 + 2 * IC(j) + 1);
+        });
+    });
+    sfor<4>([&](auto j) {
+        float2 c[8];
+        sfor<8>([&](auto k) { c[IC(k)] = p[IC(k)][IC(j)]; });
+        sfor<4>([&](auto n) {
+            float2 e = fmul2(c[0], bc(m.t[IC(n)])), o = fmul2(c[1], bc(m.t[8 + IC(n)]));
+            sfor<3>([&](auto i) {
+                e = ffma2(c[2 + 2 * IC(i)], bc(m.t[(2 + 2 * IC(i)) * 8 + IC(n)]), e);
+                o = ffma2(c[3 + 2 * IC(i)], bc(m.t[(3 + 2 * IC(i)) * 8 + IC(n)]), o);
+            });
+            p[IC(n)][IC(j)] = fadd2(e, o);
+            p[7 - IC(n)][IC(j)] = fsub2(e, o);
+        });
+    });
+    sfor<8>([&](auto y) {
+        float x[8];
+        sfor<4>([&](auto n) {
+            float2 eo = ffma2(p[IC(y)][0], m.eo[IC(n)], make_float2(128.0f, 0.0f));
+            sfor<3>([&](auto i) { eo = ffma2(p[IC(y)][1 + IC(i)], m.eo[(1 + IC(i)) * 4 + IC(n)], eo); });
+            x[IC(n)] = eo.x + eo.y;
+            x[7 - IC(n)] = eo.x - eo.y;
+        });
+        sfor<4>([&](auto j) { p[IC(y)][IC(j)] = make_float2(x[2 * IC(j)], x[2 * IC(j) + 1]); });
     });
 }
 

@@ -21,6 +21,10 @@
 namespace b200dct {
 
 enum { MODE_FWD = 0, MODE_INV = 1, MODE_RT = 2 };
+// which transform arithmetic a kernel is compiled for: any dense T as ordered FMA chains, Haweel's
+// T as compile-time constants (the reference's chains minus the zero terms), or a dense T with
+// symmetric even / antisymmetric odd rows evaluated through its even/odd halves (dct_core.cuh)
+enum { TK_DENSE = 0, TK_HAWEEL = 1, TK_DENSE_SYM = 2 };
 // DT_I16ZZ: compact coefficient stream, block-major -- block (r, c) of the H/8 x W/8 grid is 64
 // consecutive int16 in JPEG zig-zag order at byte offset r*pitch + c*128 (direct family only)
 enum { DT_F32 = 0, DT_U8 = 1, DT_I16 = 2, DT_I16ZZ = 3, DT_NONE = -1 };
@@ -57,9 +61,16 @@ struct QSel<Q_PARAM_DIV> {
 
 // Runs the selected stages on a block held in p.
 //   FWD: pixels-128 -> C      INV: C -> R      RT: pixels-128 -> (C via emit_coef) -> R
-template <int MODE, bool SPARSE, int QMODE, bool CBANK, class EmitCoef>
+// FINV: the factored (+-1 LSB) inverse of dct_core.cuh instead of the reference's ordered chains;
+// it leaves pixels WITH the +128 already added (callers must not add it again).
+// Kernels whose inverse leaves the +128 already added: the factored inverse and the symmetric dense T.
+__host__ __device__ constexpr bool inverse_is_biased(int tk, bool finv) { return finv || tk == TK_DENSE_SYM; }
+
+template <int MODE, int TK, int QMODE, bool CBANK, bool FINV = false, class EmitCoef>
 __device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams &cp, EmitCoef &&emit_coef)
 {
+    constexpr bool SPARSE = TK == TK_HAWEEL;
+    static_assert(!FINV || (SPARSE && MODE != MODE_FWD && KeepOf<QMODE>::type::all), "factored inverse: Haweel's T, runtime masks only");
     auto qp = QSel<QMODE>::make(cp.q);
     // a compile-time mask prunes the forward; the inverse may rely on it only when it consumes
     // the coefficients this very thread produced (fused round trip)
@@ -67,11 +78,14 @@ __device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams 
     static_assert(KM::all || (SPARSE && MODE == MODE_RT), "compile-time masks: sparse fused round trips only");
     if constexpr (MODE != MODE_INV) {
         if constexpr (SPARSE) forward_block<KM>(p, HaweelT<false, CBANK>{}, qp);
+        else if constexpr (TK == TK_DENSE_SYM) forward_block_sym(p, cp.t, qp);
         else forward_block(p, RuntimeT<false>(cp.t), qp);
     }
     if constexpr (MODE == MODE_RT) emit_coef(p);
     if constexpr (MODE != MODE_FWD) {
-        if constexpr (SPARSE) inverse_block<KM>(p, HaweelT<true, CBANK>{}, qp);
+        if constexpr (FINV) inverse_block_fast<true>(p, qp);
+        else if constexpr (SPARSE) inverse_block<KM>(p, HaweelT<true, CBANK>{}, qp);
+        else if constexpr (TK == TK_DENSE_SYM) inverse_block_sym(p, cp.t, qp);
         else inverse_block(p, RuntimeT<true>(cp.t), qp);
     }
 }
@@ -118,6 +132,13 @@ __device__ __forceinline__ uint2 pack_u8_plus128(const float2 (&r)[4])
     uint2 w;
     w.x = pack4_u8(r[0].x + 128.0f, r[0].y + 128.0f, r[1].x + 128.0f, r[1].y + 128.0f);
     w.y = pack4_u8(r[2].x + 128.0f, r[2].y + 128.0f, r[3].x + 128.0f, r[3].y + 128.0f);
+    return w;
+}
+__device__ __forceinline__ uint2 pack_u8_row(const float2 (&r)[4]) // pixels that already carry the +128
+{
+    uint2 w;
+    w.x = pack4_u8(r[0].x, r[0].y, r[1].x, r[1].y);
+    w.y = pack4_u8(r[2].x, r[2].y, r[3].x, r[3].y);
     return w;
 }
 __device__ __forceinline__ uint4 pack_i16(const float2 (&r)[4])
@@ -201,9 +222,10 @@ __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
 #ifndef B200DCT_DIRECT_MIN_BLOCKS
 #define B200DCT_DIRECT_MIN_BLOCKS 5
 #endif
-template <int MODE, bool SPARSE, int QMODE, int PIX, bool METRICS = false>
+template <int MODE, int TK, int QMODE, int PIX, bool METRICS = false, bool FINV = false>
 __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) k_direct(const __grid_constant__ DirectParams P)
 {
+    constexpr bool BIASED = inverse_is_biased(TK, FINV);
     // CTA = 32 block-columns x 4 block-rows; grid.x walks block-rows (no 65535 limit),
     // grid.y walks groups of 32 block-columns.  Lanes of a warp are horizontally adjacent
     // blocks, so each row access of a warp covers one contiguous 1 KiB segment.
@@ -275,7 +297,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         }
     };
 
-    run_block<MODE, SPARSE, QMODE, true>(p, P.cp, [&](float2 (&c)[8][4]) {
+    run_block<MODE, TK, QMODE, true, FINV>(p, P.cp, [&](float2 (&c)[8][4]) {
         if (P.coef && valid) store_coef(P.coef, P.coef_pitch, c);
         if constexpr (METRICS) {
             sfor<8>([&](auto r) {
@@ -294,7 +316,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 32;
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
         sfor<8>([&](auto r) {
-            shift_row(p[IC(r)], 128.0f); // add_matrix_scalar, utils_kernels.cu:29
+            if constexpr (!BIASED) shift_row(p[IC(r)], 128.0f); // add_matrix_scalar, utils_kernels.cu:29
             if (valid) st_row_f32(dst + IC(r) * P.out_pitch, p[IC(r)]);
             if constexpr (METRICS) {
                 float2 x[4];
@@ -310,7 +332,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 8;
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
         sfor<8>([&](auto r) {
-            const uint2 w = pack_u8_plus128(p[IC(r)]);
+            const uint2 w = BIASED ? pack_u8_row(p[IC(r)]) : pack_u8_plus128(p[IC(r)]);
             if (valid) *reinterpret_cast<uint2 *>(dst + IC(r) * P.out_pitch) = w;
             if constexpr (METRICS) {
                 // integers: sum (x-y)^2 = sum x^2 - 2 sum x*y + sum y^2, four pixels per IDP.4A
@@ -361,9 +383,10 @@ struct AnyParams {
     CommonParams cp;
 };
 
-template <bool SPARSE, int QMODE, int PIX>
+template <int TK, int QMODE, int PIX, bool FINV = false>
 __global__ void __launch_bounds__(128, 5) k_any(const __grid_constant__ AnyParams P)
 {
+    constexpr bool BIASED = inverse_is_biased(TK, FINV);
     using elem_t = typename std::conditional<PIX == DT_F32, float, uint8_t>::type;
     __shared__ __align__(16) uint32_t stage[4][8 * 256];
     const int lane = threadIdx.x;
@@ -392,15 +415,16 @@ __global__ void __launch_bounds__(128, 5) k_any(const __grid_constant__ AnyParam
     });
     __syncwarp(); // every lane has its block: the stage can take the results
 
-    run_block<MODE_RT, SPARSE, QMODE, true>(p, P.cp, [](float2 (&)[8][4]) {});
+    run_block<MODE_RT, TK, QMODE, true, FINV>(p, P.cp, [](float2 (&)[8][4]) {});
 
     // blocks -> stage: the final element value (f32 bits, or the u8 value) per pixel
     auto fin = [](float v) -> uint32_t {
+        const float o = BIASED ? v : v + 128.0f; // add_matrix_scalar, utils_kernels.cu:29
         if constexpr (PIX == DT_F32) {
-            return __float_as_uint(v + 128.0f); // add_matrix_scalar, utils_kernels.cu:29
+            return __float_as_uint(o);
         } else {
             uint32_t b;
-            asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(v + 128.0f)); // convertToUnsignedChar, utils.cu:21
+            asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(o)); // convertToUnsignedChar, utils.cu:21
             return b;
         }
     };
@@ -581,18 +605,23 @@ __device__ __forceinline__ uint32_t tile_bytes()
 #ifndef B200DCT_TMA_CTA_THREADS_DENSE
 #define B200DCT_TMA_CTA_THREADS_DENSE 384
 #endif
+#ifndef B200DCT_TMA_CTA_THREADS_SYM
+#define B200DCT_TMA_CTA_THREADS_SYM 384
+#endif
 #ifndef B200DCT_TMA_DEFAULT_WARPS
 #define B200DCT_TMA_DEFAULT_WARPS 8
 #endif
-__host__ __device__ constexpr int tma_cta_threads(int pix, bool sparse)
+__host__ __device__ constexpr int tma_cta_threads(int pix, int tk)
 {
-    return pix == DT_U8 ? B200DCT_TMA_CTA_THREADS_U8 : (sparse ? B200DCT_TMA_CTA_THREADS : B200DCT_TMA_CTA_THREADS_DENSE);
+    return pix == DT_U8 ? B200DCT_TMA_CTA_THREADS_U8
+                        : (tk == TK_HAWEEL ? B200DCT_TMA_CTA_THREADS : (tk == TK_DENSE_SYM ? B200DCT_TMA_CTA_THREADS_SYM : B200DCT_TMA_CTA_THREADS_DENSE));
 }
-#define B200DCT_TMA_BOUNDS __launch_bounds__(tma_cta_threads(PIX, SPARSE), 1)
+#define B200DCT_TMA_BOUNDS __launch_bounds__(tma_cta_threads(PIX, TK), 1)
 
-template <int MODE, bool SPARSE, int QMODE, int PIX>
+template <int MODE, int TK, int QMODE, int PIX, bool FINV = false>
 __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
 {
+    constexpr bool BIASED = inverse_is_biased(TK, FINV);
     extern __shared__ uint8_t smem_raw[];
     // 1 KiB alignment: the 128B swizzle pattern is a function of address bits 7..9
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -700,7 +729,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             }
         };
 
-        run_block<MODE, SPARSE, QMODE, true>(p, P.cp, [&](float2 (&c)[8][4]) {
+        run_block<MODE, TK, QMODE, true, FINV>(p, P.cp, [&](float2 (&c)[8][4]) {
             if (P.has_coef) put_coef_tile(&P.coef_map, c);
         });
 
@@ -711,10 +740,10 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
             if constexpr (PIX == DT_F32) {
-                sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); });
+                if constexpr (!BIASED) sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); });
                 tile_st_f32(out_buf, off0, p);
             } else {
-                sfor<8>([&](auto r) { sts64u(out_buf + IC(r) * 256 + lane * 8, pack_u8_plus128(p[IC(r)])); });
+                sfor<8>([&](auto r) { sts64u(out_buf + IC(r) * 256 + lane * 8, BIASED ? pack_u8_row(p[IC(r)]) : pack_u8_plus128(p[IC(r)])); });
             }
             fence_async_smem();
             __syncwarp();

@@ -8,8 +8,8 @@ namespace b200dct {
 #define B200_CAT_(a, b) a##b
 #define B200_CAT(a, b) B200_CAT_(a, b)
 
-#define B200_DIRECT_CASE(M, X)                                                      \
-    if (mode == (M) && pix == (X)) {                                                \
+#define B200_DIRECT_CASE(M, X, F)                                                   \
+    if (mode == (M) && pix == (X) && finv == (F)) {                                 \
         cudaLaunchConfig_t cfg = {};                                                \
         cfg.gridDim = grid;                                                         \
         cfg.blockDim = block;                                                       \
@@ -20,31 +20,45 @@ namespace b200dct {
         attr[0].val.programmaticStreamSerializationAllowed = 1;                     \
         cfg.attrs = attr;                                                           \
         cfg.numAttrs = pdl ? 1 : 0;                                                 \
-        return cudaLaunchKernelEx(&cfg, k_direct<M, INST_SPARSE, INST_Q, X>, P);    \
+        return cudaLaunchKernelEx(&cfg, k_direct<M, INST_SPARSE, INST_Q, X, false, F>, P); \
     }
 
-cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
 {
-    B200_DIRECT_CASE(MODE_RT, DT_F32)
-    B200_DIRECT_CASE(MODE_RT, DT_U8)
+    // finv: factored +-1 LSB inverse (Haweel's T, 8-bit pixel output only)
+    B200_DIRECT_CASE(MODE_RT, DT_F32, false)
+    B200_DIRECT_CASE(MODE_RT, DT_U8, false)
+#if INST_SPARSE == 1
+    B200_DIRECT_CASE(MODE_RT, DT_U8, true)
+#endif
 #ifdef B200DCT_FAST_BUILD /* experiment builds: round trip only (+ f32 split for the default quantiser) */
 #if INST_Q == 0
-    B200_DIRECT_CASE(MODE_FWD, DT_F32)
-    B200_DIRECT_CASE(MODE_INV, DT_F32)
+    B200_DIRECT_CASE(MODE_FWD, DT_F32, false)
+    B200_DIRECT_CASE(MODE_INV, DT_F32, false)
 #endif
     return cudaErrorInvalidValue;
 #else
-    B200_DIRECT_CASE(MODE_FWD, DT_F32)
-    B200_DIRECT_CASE(MODE_FWD, DT_U8)
-    B200_DIRECT_CASE(MODE_INV, DT_F32)
-    B200_DIRECT_CASE(MODE_INV, DT_U8)
+    B200_DIRECT_CASE(MODE_FWD, DT_F32, false)
+    B200_DIRECT_CASE(MODE_FWD, DT_U8, false)
+    B200_DIRECT_CASE(MODE_INV, DT_F32, false)
+    B200_DIRECT_CASE(MODE_INV, DT_U8, false)
+#if INST_SPARSE == 1
+    B200_DIRECT_CASE(MODE_INV, DT_U8, true)
+#endif
     return cudaErrorInvalidValue;
 #endif
 }
 
-cudaError_t B200_CAT(launch_direct_metrics_, INST_TAG)(int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
+cudaError_t B200_CAT(launch_direct_metrics_, INST_TAG)(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
 {
 #ifndef B200DCT_FAST_BUILD
+#if INST_SPARSE == 1
+    if (pix == DT_U8 && finv) {
+        k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_U8, true, true><<<grid, block, 0, s>>>(P);
+        return cudaGetLastError();
+    }
+#endif
+    if (finv) return cudaErrorInvalidValue;
     if (pix == DT_F32) {
         k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_F32, true><<<grid, block, 0, s>>>(P);
         return cudaGetLastError();

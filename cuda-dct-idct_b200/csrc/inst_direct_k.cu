@@ -19,7 +19,7 @@ static cudaError_t launch_one(const DirectParams &P, dim3 grid, dim3 block, cuda
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_direct<MODE_RT, true, QM, PIX>, P);
+    return cudaLaunchKernelEx(&cfg, k_direct<MODE_RT, TK_HAWEEL, QM, PIX>, P);
 }
 
 template <int PIX>

@@ -6,9 +6,9 @@ namespace b200dct {
 #define B200_CAT_(a, b) a##b
 #define B200_CAT(a, b) B200_CAT_(a, b)
 
-#define B200_TMA_CASE(M, X)                                                                           \
-    if (mode == (M) && pix == (X)) {                                                                  \
-        auto kern = k_tma<M, INST_SPARSE, INST_Q, X>;                                                 \
+#define B200_TMA_CASE(M, X, F)                                                                        \
+    if (mode == (M) && pix == (X) && finv == (F)) {                                                   \
+        auto kern = k_tma<M, INST_SPARSE, INST_Q, X, F>;                                              \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
         cudaLaunchConfig_t cfg = {};                                                                  \
@@ -24,21 +24,27 @@ namespace b200dct {
         return cudaLaunchKernelEx(&cfg, kern, P);                                                     \
     }
 
-cudaError_t B200_CAT(launch_tma_, INST_TAG)(int mode, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl)
+cudaError_t B200_CAT(launch_tma_, INST_TAG)(int mode, int pix, bool finv, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl)
 {
-    B200_TMA_CASE(MODE_RT, DT_F32)
-    B200_TMA_CASE(MODE_RT, DT_U8)
+    B200_TMA_CASE(MODE_RT, DT_F32, false)
+    B200_TMA_CASE(MODE_RT, DT_U8, false)
+#if INST_SPARSE == 1
+    B200_TMA_CASE(MODE_RT, DT_U8, true)
+#endif
 #ifdef B200DCT_FAST_BUILD
 #if INST_Q == 0
-    B200_TMA_CASE(MODE_FWD, DT_F32)
-    B200_TMA_CASE(MODE_INV, DT_F32)
+    B200_TMA_CASE(MODE_FWD, DT_F32, false)
+    B200_TMA_CASE(MODE_INV, DT_F32, false)
 #endif
     return cudaErrorInvalidValue;
 #else
-    B200_TMA_CASE(MODE_FWD, DT_F32)
-    B200_TMA_CASE(MODE_FWD, DT_U8)
-    B200_TMA_CASE(MODE_INV, DT_F32)
-    B200_TMA_CASE(MODE_INV, DT_U8)
+    B200_TMA_CASE(MODE_FWD, DT_F32, false)
+    B200_TMA_CASE(MODE_FWD, DT_U8, false)
+    B200_TMA_CASE(MODE_INV, DT_F32, false)
+    B200_TMA_CASE(MODE_INV, DT_U8, false)
+#if INST_SPARSE == 1
+    B200_TMA_CASE(MODE_INV, DT_U8, true)
+#endif
     return cudaErrorInvalidValue;
 #endif
 }

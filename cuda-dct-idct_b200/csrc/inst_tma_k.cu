@@ -8,7 +8,7 @@ namespace b200dct {
 template <int QM, int PIX>
 static cudaError_t launch_one(const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl)
 {
-    auto kern = k_tma<MODE_RT, true, QM, PIX>;
+    auto kern = k_tma<MODE_RT, TK_HAWEEL, QM, PIX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};

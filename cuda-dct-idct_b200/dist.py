@@ -70,6 +70,20 @@ def sum_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
+def all_ranks(value: float, device=None) -> list:
+    """The scalar of every rank, in rank order (per-rank timing diagnostics)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [float(value)]
+    dev = device or ("cuda" if dist.get_backend() == "nccl" else "cpu")
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(x.item()) for x in out]
+
+
 def my_stripe(H: int):
     rank, _, world = env_rank()
     return stripe_rows(H, world, rank)

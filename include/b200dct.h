@@ -80,6 +80,43 @@ typedef enum b200dct_path {
     B200DCT_PATH_TMA = 2     /* per-warp TMA tiles through swizzled shared memory */
 } b200dct_path;
 
+/* How the INVERSE transform is evaluated when Haweel's T is in use.
+ *   EXACT    : the reference's ordered FMA chains (cuda_matrix_idct, main_newAppr.cu:236-239,246-248):
+ *              f32 pixels bit-identical to the reference kernels, u8 pixels bit-identical to
+ *              convertToUnsignedChar (utils.cu:21) of them.
+ *   FACTORED : even/odd butterfly factorisation of T^T (21 operations per 8-point transform instead
+ *              of 44 FMAs).  Same mathematics, sums re-associated: the float value differs from the
+ *              chain in its last bits, so an 8-bit pixel differs from the reference's by at most
+ *              1 LSB, and only where the value lies within ~1e-4 of an integer (measured fraction:
+ *              tests/test_gpu_factored.py).  Applies to 8-bit pixel OUTPUT only;
+ *              f32 pixel output always uses the chains.  The forward transform and the quantiser
+ *              are never factored: quantised coefficients are bit-exact in every mode.
+ *   AUTO     : FACTORED where it applies (8-bit output: the contract there is +-1 LSB), else EXACT.
+ * Default AUTO. */
+typedef enum b200dct_inverse_mode {
+    B200DCT_INVERSE_AUTO = 0,
+    B200DCT_INVERSE_EXACT = 1,
+    B200DCT_INVERSE_FACTORED = 2
+} b200dct_inverse_mode;
+
+/* How a DENSE T (anything that is not bit-identical to Haweel's matrix: the "exact DCT" of the
+ * cublasDCT / cublasDCTv2 variants, main_cublass.cu:85-93) is evaluated.
+ *   CHAIN     : every inner product as the ascending chain of 8 FMAs (the order of the reference's
+ *               non-cuBLAS kernels; bit-identical to oracle/dct_oracle.c with that T).
+ *   SYMMETRIC : if T's even rows are symmetric and its odd rows antisymmetric (T[k][n] == +-T[k][7-n],
+ *               true of the DCT-II), evaluate it through its even/odd halves: 40 instead of 64
+ *               operations per 8-point transform in both directions.  Sums are re-associated; the
+ *               reference for dense T is cuBLAS, whose own accumulation order is undocumented and
+ *               already differs from any fixed chain in 1e-4..1e-3 of the quantised coefficients, so
+ *               the criterion is the mismatch COUNT against live cuBLAS (tests/test_gpu_reference.py),
+ *               pixels within 1 LSB.  A T without the structure runs CHAIN.
+ *   AUTO      : SYMMETRIC where T has the structure.  Default. */
+typedef enum b200dct_dense_mode {
+    B200DCT_DENSE_AUTO = 0,
+    B200DCT_DENSE_CHAIN = 1,
+    B200DCT_DENSE_SYMMETRIC = 2
+} b200dct_dense_mode;
+
 typedef struct b200dct_plan b200dct_plan;
 
 /* A plan owns the small state the reference keeps in globals: T (64 floats), Q (64
@@ -109,6 +146,11 @@ int b200dct_plan_set_keep_mask(b200dct_plan *plan, uint64_t mask);
 uint64_t b200dct_zigzag_mask(int k);
 
 int b200dct_plan_set_path(b200dct_plan *plan, b200dct_path path);
+int b200dct_plan_set_inverse(b200dct_plan *plan, b200dct_inverse_mode mode);
+int b200dct_plan_set_dense(b200dct_plan *plan, b200dct_dense_mode mode);
+/* Which arithmetic the plan's kernels use: 0 ordered chains (dense T), 1 Haweel's sparse
+ * compile-time kernels, 2 symmetric dense kernels. */
+int b200dct_plan_kernel_kind(const b200dct_plan *plan);
 /* 1 if the plan's T is Haweel's matrix (sparse kernels), 0 if dense. */
 int b200dct_plan_is_sparse(const b200dct_plan *plan);
 

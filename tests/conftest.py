@@ -11,6 +11,29 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: long-running GPU sweep")
+    config.addinivalue_line("markers", "factored: runs with the library's DEFAULT arithmetic modes (factored +-1 LSB inverse for "
+                                       "8-bit output, even/odd evaluation of symmetric dense T); every other test pins "
+                                       "B200DCT_INVERSE=exact B200DCT_DENSE=chain and compares bit for bit")
+
+
+@pytest.fixture(autouse=True)
+def _inverse_mode(request, monkeypatch):
+    """u8 pixels are compared BIT-EXACT against the oracle in most tests, which is the contract of
+    the EXACT inverse (the reference's FMA chains).  The library default for 8-bit output is the
+    factored inverse (+-1 LSB): tests marked `factored` exercise that default."""
+    if request.node.get_closest_marker("factored") is None:
+        monkeypatch.setenv("B200DCT_INVERSE", "exact")
+        monkeypatch.setenv("B200DCT_DENSE", "chain")    # dense T as ordered chains == the oracle, bit for bit
+    else:
+        monkeypatch.delenv("B200DCT_INVERSE", raising=False)
+        monkeypatch.delenv("B200DCT_DENSE", raising=False)
+    mod = sys.modules.get("cuda_dct_idct_b200")
+    if mod is not None:
+        mod.api._default_plan = None   # the cached default plan was created under the other mode
+    yield
+    mod = sys.modules.get("cuda_dct_idct_b200")
+    if mod is not None:
+        mod.api._default_plan = None
 
 
 @pytest.fixture(scope="session")

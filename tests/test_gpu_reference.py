@@ -62,6 +62,40 @@ def test_reference_kernels_pin_the_oracle(oracle, dct, variant, N):
     assert m_new[0] == pytest.approx(m_ref[0], rel=1e-12) and m_new[1] == pytest.approx(m_ref[1], rel=1e-12)
 
 
+def test_headline_size_whole_image_against_the_reference_kernel(oracle, dct):
+    """BASELINE configs[1] compared WHOLE: every coefficient and every f32 pixel of the 8192^2
+    image against the unmodified reference kernels (3.3 ms on the box), plus SURVEY.md
+    Appendix B's N=8192 known answers on the GPU results."""
+    need("newappr")
+    N = 8192
+    img = oracle.rand_image(N, N, 42)                       # srand(42); rand()%256
+    T = dev(oracle.haweel_T())
+    refgpu.set_quant("newappr", oracle.jpeg_Q())
+    work = dev(img)
+    ref_coef, _ = refgpu.dct("newappr", work, T)
+    ref_rec, _ = refgpu.idct("newappr", ref_coef, T)
+    d = dev(img)
+    for path in (2, 1):
+        plan = dct.Plan(path=path)
+        coef = torch.empty_like(d)
+        out = dct.roundtrip(d, coef=coef, plan=plan)
+        assert torch.equal(coef.view(torch.int32), ref_coef.view(torch.int32)), path
+        assert torch.equal(out.view(torch.int32), ref_rec.view(torch.int32)), path
+        del coef
+    # the split entry points (the drop-in two-call API) as well
+    c2 = dct.forward(d)
+    assert torch.equal(c2.view(torch.int32), ref_coef.view(torch.int32))
+    assert torch.equal(dct.inverse(c2).view(torch.int32), ref_rec.view(torch.int32))
+    # Appendix B, N = 8192
+    assert int(ref_coef.double().sum().item()) == -268447
+    assert int(ref_coef.abs().double().sum().item()) == 117045095
+    assert int((ref_coef != 0).sum().item()) == 47462419
+    u8 = out.clamp(0, 255).to(torch.uint8)
+    assert int(u8.long().sum().item()) == 8524699637
+    mse, peen = dct.metrics(d.to(torch.uint8), u8)
+    assert mse == pytest.approx(344.379744306, rel=1e-9) and peen == pytest.approx(12.593068395, rel=1e-9)
+
+
 def test_reference_on_adversarial_and_rectangular(oracle, dct):
     need("newappr")
     T = dev(oracle.haweel_T())
@@ -117,6 +151,39 @@ def test_cublas_variants_mismatch_count(oracle, dct, variant):
         b = dct.metrics(u8, ref_rec.clamp(0, 255).to(torch.uint8))
         assert a[0] == pytest.approx(b[0], rel=1e-3) and a[1] == pytest.approx(b[1], rel=1e-3)
         assert int((rec.clamp(0, 255).to(torch.uint8).int() - ref_rec.clamp(0, 255).to(torch.uint8).int()).abs().max()) <= 1
+
+
+@pytest.mark.factored
+@pytest.mark.parametrize("N", [1024, 2048])
+def test_cublas2_mismatch_counts_at_larger_sizes(oracle, dct, N):
+    """cublasDCTv2 (whole-image Sgemm, main_cublass_2.cu:228-235,288-295) at 1024^2 and 2048^2 with
+    the true DCT-II matrix: mismatch count of the quantised coefficients for BOTH dense modes
+    (ordered chains, and the default even/odd evaluation) -- the even/odd kernel must be no
+    further from cuBLAS than the chain kernel is, pixels within 1 LSB, MSE/PEEN within 1e-3."""
+    need("cublas2")
+    img = oracle.rand_image(N, N, 42)
+    Tm = oracle.dct2_T()
+    refgpu.set_quant("cublas2", oracle.jpeg_Q())
+    T = dev(Tm)
+    ref_coef, _ = refgpu.dct("cublas2", dev(img), T)
+    keep = ref_coef.clone()
+    ref_rec, _ = refgpu.idct("cublas2", ref_coef, T)       # dequantises ref_coef in place
+    counts = {}
+    for name, mode in (("chain", dct.api.DENSE_CHAIN), ("symmetric", dct.api.DENSE_AUTO)):
+        plan = dct.Plan(T=Tm, dense=mode)
+        coef = dct.forward(dev(img), plan=plan)
+        counts[name] = int((coef != keep).sum())
+        assert float((coef - keep).abs().max()) <= 1
+        rec = dct.inverse(keep, plan=plan)
+        assert float((rec - ref_rec).abs().max()) < 1e-3
+        u8 = dev(img).to(torch.uint8)
+        a = dct.metrics(u8, rec.clamp(0, 255).to(torch.uint8))
+        b = dct.metrics(u8, ref_rec.clamp(0, 255).to(torch.uint8))
+        assert a[0] == pytest.approx(b[0], rel=1e-3) and a[1] == pytest.approx(b[1], rel=1e-3)
+        assert int((rec.clamp(0, 255).to(torch.uint8).int() - ref_rec.clamp(0, 255).to(torch.uint8).int()).abs().max()) <= 1
+    print(f"[cublas2/dct2 {N}^2] coefficient mismatches vs live cuBLAS: chain {counts['chain']}, "
+          f"even/odd {counts['symmetric']} of {N * N}")
+    assert counts["symmetric"] <= max(2 * counts["chain"], 1e-3 * N * N)
 
 
 def test_committed_reference_fixtures_match_live_reference(oracle):

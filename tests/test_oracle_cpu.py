@@ -28,10 +28,11 @@ def test_constants_bit_patterns(oracle):
     # SURVEY.md Appendix B (reference generator srand(42), rand()%256)
     (256, -306, 114414, 46317, 8329775, 342.731643677, 12.552802314),
     (1024, -2562, 1831230, 741557, 133161285, 344.862137794, 12.604274134),
+    (8192, -268447, 117045095, 47462419, 8524699637, 344.379744306, 12.593068395),   # the headline size
 ])
 def test_known_answers(oracle, N, s, sa, nz, su8, mse, peen):
     img = oracle.rand_image(N, N, 42)
-    out, coef = oracle.roundtrip(img, want_coef=True)
+    out, coef = oracle.roundtrip(img, want_coef=True, threads=max(1, min(8, os.cpu_count() or 1)))
     assert int(coef.sum(dtype=np.float64)) == s
     assert int(np.abs(coef).sum(dtype=np.float64)) == sa
     assert int(np.count_nonzero(coef)) == nz
