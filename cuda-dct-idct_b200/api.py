@@ -155,7 +155,7 @@ class Plan:
         _check(lib().b200dct_plan_set_inverse(self._h, mode))
 
     def set_dense(self, mode: int) -> None:
-        """DENSE_CHAIN: ordered FMA chains for a dense T (bit-identical to the oracle with that T);
+        """DENSE_CHAIN: ordered FMA chains for a dense T (bit-identical to the reference's chain order with that T);
         DENSE_AUTO / DENSE_SYMMETRIC: even/odd evaluation when T has the DCT-II symmetry."""
         _check(lib().b200dct_plan_set_dense(self._h, mode))
 
