@@ -208,10 +208,30 @@ def _plane(t):
     if t.dim() == 3:  # B x H x W stored back to back == one (B*H) x W image
         if not t.is_contiguous():
             raise B200DCTError("batched tensors must be contiguous")
+        if t.shape[-2] % 8:
+            raise B200DCTError("batched images need a height that is a multiple of 8 (blocks must not straddle images)")
         t = t.view(-1, t.shape[-1])
     if t.dim() != 2 or t.stride(1) != 1:
         raise B200DCTError("expected a row-major 2-d tensor")
     return t.data_ptr(), _dt(t), t.stride(0) * t.element_size(), t.shape[0], t.shape[1]
+
+
+def _same_plane(t, H, W, what, dtypes=None):
+    """_plane(t) for a tensor that must describe the same H x W image: the C side trusts H, W and
+    the pitch, so a smaller or differently shaped tensor would mean out-of-bounds device writes."""
+    p, dt, pitch, h, w = _plane(t)
+    if (h, w) != (H, W):
+        raise B200DCTError(f"{what}: shape {tuple(t.shape)} does not describe the {H}x{W} image of the call")
+    if dtypes is not None and t.dtype not in dtypes:
+        raise B200DCTError(f"{what}: dtype {t.dtype} not allowed here")
+    return p, dt, pitch
+
+
+def _zz_same(t, H, W, what):
+    p, dt, pitch, h, w = _zz_plane(t)
+    if (h, w) != (H, W):
+        raise B200DCTError(f"{what}: stream shape {tuple(t.shape)} does not match the {H}x{W} image")
+    return p, dt, pitch
 
 
 def _zz_plane(t):
@@ -238,17 +258,45 @@ def _stream(stream):
     return C.c_void_p(s.cuda_stream)
 
 
+class _on:
+    """Scope of one call: the tensor's device and the caller's stream are made current, so that
+    every allocation, launch and read-back of the call is ordered on ONE stream (torch's caching
+    allocator ties a block to the stream that was current when it was allocated)."""
+
+    def __init__(self, t, stream):
+        import torch
+
+        self._dev = torch.cuda.device(t.device)
+        self._st = torch.cuda.stream(stream) if stream is not None else None
+
+    def __enter__(self):
+        self._dev.__enter__()
+        if self._st is not None:
+            self._st.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self._st is not None:
+            self._st.__exit__(*a)
+        return self._dev.__exit__(*a)
+
+
 def forward(img, coef=None, plan: Plan | None = None, coef_dtype=None, shifted=None, stream=None, zigzag=False):
     """coef = round(T.(img-128).T^T / Q); img f32|u8 CUDA tensor; coef f32 (default) or int16 plane,
     or (zigzag=True) the block-major int16 zig-zag stream of shape (H/8, W/8, 64)."""
     import torch
 
     ip, idt, ipitch, H, W = _plane(img)
-    if coef is None:
-        coef = empty_zigzag(H, W, img.device) if zigzag else torch.empty(img.shape, dtype=coef_dtype or torch.float32, device=img.device)
-    cp, cdt, cpitch, _, _ = _zz_plane(coef) if zigzag else _plane(coef)
-    sp = _plane(shifted)[0] if shifted is not None else None
-    with torch.cuda.device(img.device):
+    with _on(img, stream):
+        if coef is None:
+            coef = empty_zigzag(H, W, img.device) if zigzag else torch.empty(img.shape, dtype=coef_dtype or torch.float32, device=img.device)
+        cp, cdt, cpitch = _zz_same(coef, H, W, "coef") if zigzag else _same_plane(coef, H, W, "coef", (torch.float32, torch.int16))
+        sp = None
+        if shifted is not None:
+            # the C side writes img-128 as f32 with the INPUT's pitch (b200dct_forward)
+            sp, _, spitch = _same_plane(shifted, H, W, "shifted", (torch.float32,))
+            if img.dtype != torch.float32 or spitch != ipitch:
+                raise B200DCTError("shifted: needs a float32 image and a float32 buffer with the image's row pitch")
         _check(lib().b200dct_forward(_plan(plan)._h, ip, idt, ipitch, cp, cdt, cpitch, sp, H, W, _stream(stream)))
     return coef
 
@@ -259,10 +307,10 @@ def inverse(coef, img=None, plan: Plan | None = None, img_dtype=None, stream=Non
     import torch
 
     cp, cdt, cpitch, H, W = _zz_plane(coef) if zigzag else _plane(coef)
-    if img is None:
-        img = torch.empty((H, W) if zigzag else coef.shape, dtype=img_dtype or torch.float32, device=coef.device)
-    ip, idt, ipitch, _, _ = _plane(img)
-    with torch.cuda.device(coef.device):
+    with _on(coef, stream):
+        if img is None:
+            img = torch.empty((H, W) if zigzag else coef.shape, dtype=img_dtype or torch.float32, device=coef.device)
+        ip, idt, ipitch = _same_plane(img, H, W, "img", (torch.float32, torch.uint8))
         _check(lib().b200dct_inverse(_plan(plan)._h, cp, cdt, cpitch, ip, idt, ipitch, H, W, _stream(stream)))
     return img
 
@@ -273,14 +321,14 @@ def roundtrip(img, out=None, coef=None, plan: Plan | None = None, stream=None, z
     import torch
 
     ip, idt, ipitch, H, W = _plane(img)
-    if out is None:
-        out = torch.empty_like(img)
-    op, odt, opitch, _, _ = _plane(out)
-    if coef is not None:
-        cp, cdt, cpitch, _, _ = _zz_plane(coef) if zigzag else _plane(coef)
-    else:
-        cp, cdt, cpitch = None, F32, 0
-    with torch.cuda.device(img.device):
+    with _on(img, stream):
+        if out is None:
+            out = torch.empty_like(img)
+        op, odt, opitch = _same_plane(out, H, W, "out", (img.dtype,))
+        if coef is not None:
+            cp, cdt, cpitch = _zz_same(coef, H, W, "coef") if zigzag else _same_plane(coef, H, W, "coef", (torch.float32, torch.int16))
+        else:
+            cp, cdt, cpitch = None, F32, 0
         _check(lib().b200dct_roundtrip(_plan(plan)._h, ip, idt, ipitch, op, odt, opitch, cp, cdt, cpitch, H, W,
                                        _stream(stream)))
     return out
@@ -294,11 +342,11 @@ def roundtrip_any(img, out=None, plan: Plan | None = None, stream=None):
 
     if not (img.is_cuda and img.dim() == 2 and img.stride(1) == 1):
         raise B200DCTError("expected a row-major 2-d CUDA tensor")
-    if out is None:
-        out = torch.empty_like(img)
-    if out.shape != img.shape or out.dtype != img.dtype or out.stride(1) != 1:
-        raise B200DCTError("out must match img")
-    with torch.cuda.device(img.device):
+    with _on(img, stream):
+        if out is None:
+            out = torch.empty_like(img)
+        if not out.is_cuda or out.shape != img.shape or out.dtype != img.dtype or out.stride(1) != 1:
+            raise B200DCTError("out must match img")
         _check(lib().b200dct_roundtrip_any(_plan(plan)._h, img.data_ptr(), _dt(img), img.stride(0) * img.element_size(),
                                            out.data_ptr(), out.stride(0) * out.element_size(), img.shape[0], img.shape[1],
                                            _stream(stream)))
@@ -311,17 +359,17 @@ def roundtrip_with_metrics(img, out=None, coef=None, plan: Plan | None = None, s
     import torch
 
     ip, idt, ipitch, H, W = _plane(img)
-    if out is None:
-        out = torch.empty_like(img)
-    op, odt, opitch, _, _ = _plane(out)
-    cp, cdt, cpitch = (None, F32, 0) if coef is None else _plane(coef)[:3]
-    nbytes = int(lib().b200dct_metrics_workspace_bytes(H, W))
-    ws = torch.empty(max(1, nbytes // 8), dtype=torch.float64, device=img.device)
-    acc = torch.zeros(3, dtype=torch.float64, device=img.device)
-    with torch.cuda.device(img.device):
+    with _on(img, stream):     # workspace, zero-fill, kernels and the read-back all on the caller's stream
+        if out is None:
+            out = torch.empty_like(img)
+        op, odt, opitch = _same_plane(out, H, W, "out", (img.dtype,))
+        cp, cdt, cpitch = (None, F32, 0) if coef is None else _same_plane(coef, H, W, "coef", (torch.float32, torch.int16))
+        nbytes = int(lib().b200dct_metrics_workspace_bytes(H, W))
+        ws = torch.empty(max(1, nbytes // 8), dtype=torch.float64, device=img.device)
+        acc = torch.zeros(3, dtype=torch.float64, device=img.device)
         _check(lib().b200dct_roundtrip_metrics(_plan(plan)._h, ip, idt, ipitch, op, odt, opitch, cp, cdt, cpitch, H, W,
                                                acc.data_ptr(), ws.data_ptr(), nbytes, _stream(stream)))
-    sse, energy, nnz = acc.tolist()
+        sse, energy, nnz = acc.tolist()
     n = H * W
     return out, (sse / n, 100.0 * (sse / energy) ** 0.5 if energy > 0 else 0.0, int(nnz))
 
@@ -359,13 +407,13 @@ def metrics(ref_img, test_img, stream=None):
     import torch
 
     rp, rdt, rpitch, H, W = _plane(ref_img)
-    tp, tdt, tpitch, _, _ = _plane(test_img)
-    if rdt != tdt or rpitch != tpitch:
-        raise B200DCTError("metrics needs two images of the same dtype and pitch")
-    acc = torch.zeros(2, dtype=torch.float64, device=ref_img.device)
-    with torch.cuda.device(ref_img.device):
+    tp, tdt, tpitch = _same_plane(test_img, H, W, "test_img", (ref_img.dtype,))
+    if rdt != tdt or rpitch != tpitch or rdt not in (F32, U8):
+        raise B200DCTError("metrics needs two float32 or uint8 images of the same dtype and pitch")
+    with _on(ref_img, stream):
+        acc = torch.zeros(2, dtype=torch.float64, device=ref_img.device)
         _check(lib().b200dct_metrics_accumulate(rp, tp, rdt, rpitch, H, W, acc.data_ptr(), _stream(stream)))
-    sse, energy = acc.tolist()
+        sse, energy = acc.tolist()
     n = H * W
     return sse / n, (100.0 * (sse / energy) ** 0.5 if energy > 0 else 0.0)
 
@@ -378,8 +426,8 @@ def time_calls(which: str, a, b, c=None, plan: Plan | None = None, iters: int = 
 
     code = {"roundtrip": 0, "forward": 1, "inverse": 2, "split": 3}[which]
     ap, adt, apitch, H, W = _plane(a)
-    bp, bdt, bpitch, _, _ = _plane(b)
-    cp, cdt, cpitch = (None, F32, 0) if c is None else _plane(c)[:3]
+    bp, bdt, bpitch = _same_plane(b, H, W, "b")
+    cp, cdt, cpitch = (None, F32, 0) if c is None else _same_plane(c, H, W, "c")
     ms = C.c_float()
     with torch.cuda.device(a.device):
         _check(lib().b200dct_time_calls(_plan(plan)._h, code, ap, adt, apitch, bp, bdt, bpitch, cp, cdt, cpitch,
@@ -404,6 +452,12 @@ def _compat_call(fn, a, H, W, T, result):
             raise B200DCTError("the reference's entry points take contiguous float32 device buffers")
     if a.numel() < H * W or result.numel() < H * W or T.numel() < 64:
         raise B200DCTError("buffer smaller than H*W")
+    # the compiled wrappers keep the reference's contract (print and exit(EXIT_FAILURE) on error,
+    # main_newAppr.cu:9-17): catch here what would otherwise end the interpreter
+    if H <= 0 or W <= 0 or H % 8 or W % 8:
+        raise B200DCTError("the reference's entry points need H and W to be positive multiples of 8")
+    if a.data_ptr() % 16 or result.data_ptr() % 16 or T.data_ptr() % 4:
+        raise B200DCTError("image buffers must be 16-byte aligned")
     with torch.cuda.device(a.device):
         torch.cuda.current_stream().synchronize()  # the wrappers run on the legacy default stream
         fn(a.data_ptr(), int(H), int(W), T.data_ptr(), result.data_ptr())

@@ -153,3 +153,56 @@ def test_host_threads_are_reentrant(dct, oracle):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_api_rejects_mismatched_planes(dct):
+    """The C side trusts H, W and the pitch: the Python binding must refuse tensors that do not
+    describe the same image instead of letting the kernels write out of bounds."""
+    img = torch.zeros(64, 64, device="cuda")
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(img, out=torch.empty(32, 64, device="cuda"))
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(img, coef=torch.empty(64, 32, device="cuda"))
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(img, out=torch.empty(64, 64, device="cuda", dtype=torch.uint8))
+    with pytest.raises(dct.B200DCTError):
+        dct.forward(img, coef=torch.empty(64, 128, device="cuda"))
+    with pytest.raises(dct.B200DCTError):
+        dct.forward(img, shifted=torch.empty(64, 64, device="cuda", dtype=torch.uint8))
+    with pytest.raises(dct.B200DCTError):
+        dct.forward(img, shifted=torch.empty(64, 128, device="cuda")[:, :64])   # other pitch
+    with pytest.raises(dct.B200DCTError):
+        dct.inverse(img, img=torch.empty(8, 64, device="cuda"))
+    with pytest.raises(dct.B200DCTError):
+        dct.metrics(img, torch.zeros(64, 32, device="cuda"))
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip(torch.zeros(3, 12, 64, device="cuda"))   # blocks would straddle the images of the batch
+    with pytest.raises(dct.B200DCTError):
+        dct.roundtrip_with_metrics(img, out=torch.empty(16, 64, device="cuda"))
+    T = torch.zeros(64, device="cuda")
+    with pytest.raises(dct.B200DCTError):     # would exit() inside the compat wrapper
+        dct.dct_all_blocks_cuda(torch.zeros(100 * 100, device="cuda"), 100, 100, T, torch.zeros(100 * 100, device="cuda"))
+
+
+def test_calls_on_a_side_stream(dct, oracle):
+    """Allocation, zero-fill, launch and read-back of one call are ordered on the caller's stream
+    (the metrics accumulators used to be zeroed on torch's current stream)."""
+    img = oracle.rand_image(512, 512, 7)
+    want = oracle.roundtrip(img)
+    w_mse, w_peen = oracle.metrics(img, want)
+    d = torch.from_numpy(img).cuda()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(5):
+        # keep the current stream busy so that a zero-fill issued there would lose the race
+        busy = torch.randn(4096, 4096, device="cuda") @ torch.randn(4096, 4096, device="cuda")
+        out, (mse, peen, nnz) = dct.roundtrip_with_metrics(d, stream=side)
+        side.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        assert abs(mse - w_mse) <= 1e-6 * w_mse and abs(peen - w_peen) <= 1e-6 * w_peen
+        m2, p2 = dct.metrics(d, out, stream=side)
+        assert abs(m2 - w_mse) <= 1e-6 * w_mse and abs(p2 - w_peen) <= 1e-6 * w_peen
+        out3 = dct.roundtrip(d, stream=side)
+        side.synchronize()
+        assert np.array_equal(out3.cpu().numpy().view(np.uint32), want.view(np.uint32))
+        del busy

@@ -178,3 +178,13 @@ def test_header_is_plain_c_and_links_from_c(m, tmp_path):
     out = subprocess.run(args, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "abi_c99 ok" in out.stdout
+
+
+def test_module_cli_prints_usage():
+    """`python -m cuda_dct_idct_b200` must reach the package's __main__ (it used to be a
+    silent no-op because runpy resolves the name to the import shim)."""
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, "-m", "cuda_dct_idct_b200"], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 1 and "Usage:" in r.stderr
