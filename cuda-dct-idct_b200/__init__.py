@@ -10,6 +10,7 @@ CPU fallback -- importing works anywhere, computing requires the built library a
 from .api import (  # noqa: F401
     ALL_COEFFS,
     B200DCTError,
+    HostPipeline,
     Plan,
     dct_all_blocks,
     dct_all_blocks_cuda,
@@ -31,7 +32,7 @@ from .build import build  # noqa: F401
 from .stripes import stripe_rows  # noqa: F401
 
 __all__ = [
-    "ALL_COEFFS", "B200DCTError", "Plan", "build", "dct_all_blocks", "dct_all_blocks_cuda", "forward",
+    "ALL_COEFFS", "B200DCTError", "HostPipeline", "Plan", "build", "dct_all_blocks", "dct_all_blocks_cuda", "forward",
     "idct_all_blocks", "idct_all_blocks_cuda", "inverse", "lib", "lib_path", "metrics", "roundtrip",
     "roundtrip_any", "roundtrip_host", "roundtrip_with_metrics", "stripe_rows", "zigzag_mask",
 ]

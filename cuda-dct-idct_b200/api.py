@@ -69,6 +69,15 @@ def lib() -> C.CDLL:
         L.b200dct_roundtrip_metrics.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp, vp, sz, vp]
         L.b200dct_roundtrip_any.argtypes = [vp, vp, i, sz, vp, sz, i, i, vp]
         L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
+        L.b200dct_host_pipeline_create.argtypes = [C.POINTER(vp), sz, i]
+        L.b200dct_host_pipeline_destroy.argtypes = [vp]
+        L.b200dct_host_pipeline_destroy.restype = None
+        L.b200dct_host_pipeline_chunk_bytes.argtypes = [vp]
+        L.b200dct_host_pipeline_chunk_bytes.restype = sz
+        L.b200dct_host_pipeline_submit.argtypes = [vp, vp, vp, i, vp, i, i, i, C.POINTER(C.c_ulonglong)]
+        L.b200dct_host_pipeline_wait.argtypes = [vp, C.c_ulonglong]
+        L.b200dct_host_pipeline_drain.argtypes = [vp]
+        L.b200dct_host_pipeline_last_launch_count.argtypes = [vp]
         L.b200dct_metrics_accumulate.argtypes = [vp, vp, i, sz, i, i, vp, vp]
         L.b200dct_time_calls.argtypes = [vp, i, vp, i, sz, vp, i, sz, vp, i, sz, i, i, i, C.POINTER(C.c_float), vp]
         L.b200dct_selftest_division.argtypes = [C.c_float, C.c_ulonglong, C.c_ulonglong, vp, vp]
@@ -374,32 +383,102 @@ def roundtrip_with_metrics(img, out=None, coef=None, plan: Plan | None = None, s
     return out, (sse / n, 100.0 * (sse / energy) ** 0.5 if energy > 0 else 0.0, int(nnz))
 
 
+def _hostptr(a):
+    """(pointer, dtype code, shape) of a contiguous numpy array or CPU torch tensor."""
+    import torch
+
+    if isinstance(a, np.ndarray):
+        if not a.flags.c_contiguous:
+            raise B200DCTError("host arrays must be C-contiguous")
+        dt = {np.dtype(np.float32): F32, np.dtype(np.uint8): U8}.get(a.dtype)
+        if dt is None:
+            raise B200DCTError("host round trips take float32 or uint8 pixels")
+        return a.ctypes.data, dt, tuple(a.shape)
+    if isinstance(a, torch.Tensor) and not a.is_cuda and a.is_contiguous():
+        dt = _dt(a)
+        if dt == I16:
+            raise B200DCTError("host round trips take float32 or uint8 pixels")
+        return a.data_ptr(), dt, tuple(a.shape)
+    raise B200DCTError("expected a contiguous numpy array or CPU torch tensor")
+
+
 def roundtrip_host(h_in, h_out=None, plan: Plan | None = None):
     """Host buffers in, host buffers out (numpy arrays or pinned CPU torch tensors):
     chunked H2D -> fused kernel -> D2H pipeline inside the library.  Synchronous."""
     import torch
 
-    def hostptr(a):
-        if isinstance(a, np.ndarray):
-            if not a.flags.c_contiguous:
-                raise B200DCTError("host arrays must be C-contiguous")
-            dt = {np.dtype(np.float32): F32, np.dtype(np.uint8): U8}.get(a.dtype)
-            return a.ctypes.data, dt, a.shape
-        if isinstance(a, torch.Tensor) and not a.is_cuda and a.is_contiguous():
-            return a.data_ptr(), _dt(a), tuple(a.shape)
-        raise B200DCTError("expected a contiguous numpy array or CPU torch tensor")
-
-    ip, idt, shape = hostptr(h_in)
-    if idt is None or idt == I16:
-        raise B200DCTError("host round trip takes float32 or uint8 pixels")
+    ip, idt, shape = _hostptr(h_in)
     if h_out is None:
         h_out = np.empty_like(h_in) if isinstance(h_in, np.ndarray) else torch.empty_like(h_in)
-    op, odt, oshape = hostptr(h_out)
-    if oshape != shape:
+    op, odt, oshape = _hostptr(h_out)
+    if oshape != shape or len(shape) < 2:
         raise B200DCTError("shape mismatch")
     H = int(np.prod(shape[:-1]))
     _check(lib().b200dct_roundtrip_host(_plan(plan)._h, ip, idt, op, odt, H, int(shape[-1])))
     return h_out
+
+
+class HostPipeline:
+    """A sequence of host-buffer round trips whose images overlap (b200dct_host_pipeline_*):
+    `submit` only enqueues; `wait(ticket)` / `drain()` (or leaving the `with` block) completes.
+    Buffers must be pinned for the copies to be asynchronous and must stay alive (and `h_out`
+    unread) until waited for."""
+
+    def __init__(self, plan: Plan | None = None, chunk_bytes: int = 0, slots: int = 0):
+        self._plan = _plan(plan)
+        self._h = C.c_void_p()
+        self._keep = {}
+        _check(lib().b200dct_host_pipeline_create(C.byref(self._h), int(chunk_bytes), int(slots)))
+
+    @property
+    def chunk_bytes(self) -> int:
+        return int(lib().b200dct_host_pipeline_chunk_bytes(self._h))
+
+    def submit(self, h_in, h_out, plan: Plan | None = None) -> int:
+        ip, idt, shape = _hostptr(h_in)
+        op, odt, oshape = _hostptr(h_out)
+        if oshape != shape or len(shape) < 2:
+            raise B200DCTError("shape mismatch")
+        t = C.c_ulonglong()
+        H = int(np.prod(shape[:-1]))
+        _check(lib().b200dct_host_pipeline_submit(self._h, (plan or self._plan)._h, ip, idt, op, odt, H, int(shape[-1]), C.byref(t)))
+        self._keep[t.value] = (h_in, h_out)      # the library reads/writes them until the ticket completes
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        _check(lib().b200dct_host_pipeline_wait(self._h, int(ticket)))
+        for k in [k for k in self._keep if k <= ticket]:
+            del self._keep[k]
+
+    def drain(self) -> None:
+        _check(lib().b200dct_host_pipeline_drain(self._h))
+        self._keep.clear()
+
+    def last_launch_count(self) -> int:
+        return int(lib().b200dct_host_pipeline_last_launch_count(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().b200dct_host_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+            self._keep.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        try:
+            if a[0] is None:
+                self.drain()
+        finally:
+            self.close()
+
+    def __del__(self):
+        try:
+            if _lib is not None:
+                self.close()
+        except Exception:
+            pass
 
 
 def metrics(ref_img, test_img, stream=None):

@@ -711,93 +711,6 @@ extern "C" int b200dct_time_calls(const b200dct_plan *plan, int which, const voi
     return rc;
 }
 
-// ------------------------------------------------------------------ host-buffer round trip
-// Per-thread, per-device grow-only workspace: NCHUNK stream slots, each with an input
-// and an output chunk buffer.  Chunks are block-row stripes, so every chunk is itself a
-// valid image for the kernels (blocks are independent).
-namespace {
-constexpr int NSLOT = 4;
-struct HostPipe {
-    int dev = -1;
-    cudaStream_t st[NSLOT] = {};
-    void *din[NSLOT] = {};
-    void *dout[NSLOT] = {};
-    size_t cap_in = 0, cap_out = 0;
-    void release()
-    {
-        for (int i = 0; i < NSLOT; i++) {
-            if (din[i]) cudaFree(din[i]);
-            if (dout[i]) cudaFree(dout[i]);
-            if (st[i]) cudaStreamDestroy(st[i]);
-            din[i] = dout[i] = nullptr;
-            st[i] = nullptr;
-        }
-        cap_in = cap_out = 0;
-        dev = -1;
-    }
-    ~HostPipe() {} // device memory is reclaimed with the context
-};
-thread_local HostPipe tl_pipe;
-} // namespace
-
-extern "C" int b200dct_roundtrip_host(const b200dct_plan *plan, const void *h_in, b200dct_dtype in_dt, void *h_out,
-                                      b200dct_dtype out_dt, int H, int W)
-{
-    if (!plan || !h_in || !h_out) return B200DCT_ERR_ARG;
-    if (H <= 0 || W <= 0 || (H % 8) || (W % 8)) return B200DCT_ERR_SHAPE;
-    if (in_dt != out_dt || (in_dt != B200DCT_F32 && in_dt != B200DCT_U8)) return B200DCT_ERR_ARG;
-    int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess) return B200DCT_ERR_NODEVICE;
-    const size_t es = elem_size((int)in_dt);
-    const size_t row = (size_t)W * es;
-    // ~16 MiB chunks (env B200DCT_HOST_CHUNK_MB; best of 2..32 MiB on B200), at least 8 rows, whole
-    // block-rows.  PCIe Gen5 on the box: H2D alone 55.5 GB/s, D2H alone 57.2, both at once 49.8
-    // each; this pipeline sustains 43.4 GB/s each way (profiles/r01_pcie.txt).  Shorter chunks at
-    // both ends were tried and changed nothing.
-    static int chunk_mb = 0;
-    if (!chunk_mb) {
-        const char *e = getenv("B200DCT_HOST_CHUNK_MB");
-        chunk_mb = (e && atoi(e) >= 1 && atoi(e) <= 1024) ? atoi(e) : 16;
-    }
-    long long rows = (long long)(((size_t)chunk_mb << 20) / row) & ~7ll;
-    if (rows < 8) rows = 8;
-    if (rows > H) rows = H;
-    const size_t chunk_bytes = (size_t)rows * row;
-
-    HostPipe &hp = tl_pipe;
-    if (hp.dev != dev || hp.cap_in < chunk_bytes || hp.cap_out < chunk_bytes) {
-        hp.release();
-        for (int i = 0; i < NSLOT; i++) {
-            if (cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking) != cudaSuccess ||
-                cudaMalloc(&hp.din[i], chunk_bytes) != cudaSuccess || cudaMalloc(&hp.dout[i], chunk_bytes) != cudaSuccess) {
-                hp.release();
-                return B200DCT_ERR_NOMEM;
-            }
-        }
-        hp.cap_in = hp.cap_out = chunk_bytes;
-        hp.dev = dev;
-    }
-    int launches = 0, rc = B200DCT_OK, slot = 0;
-    for (long long r0 = 0; r0 < H; r0 += rows, slot = (slot + 1) % NSLOT) {
-        const int h = (int)((H - r0) < rows ? (H - r0) : rows);
-        const size_t bytes = (size_t)h * row;
-        cudaStream_t s = hp.st[slot];
-        cudaError_t e = cudaMemcpyAsync(hp.din[slot], (const char *)h_in + (size_t)r0 * row, bytes, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { rc = (int)e; break; }
-        rc = b200dct_roundtrip(plan, hp.din[slot], in_dt, row, hp.dout[slot], out_dt, row, nullptr, B200DCT_F32, 0, h, W, s);
-        if (rc != B200DCT_OK) break;
-        launches += tl_launches;
-        e = cudaMemcpyAsync((char *)h_out + (size_t)r0 * row, hp.dout[slot], bytes, cudaMemcpyDeviceToHost, s);
-        if (e != cudaSuccess) { rc = (int)e; break; }
-    }
-    for (int i = 0; i < NSLOT; i++) {
-        cudaError_t e = cudaStreamSynchronize(hp.st[i]);
-        if (e != cudaSuccess && rc == B200DCT_OK) rc = (int)e;
-    }
-    tl_launches = launches;
-    return rc;
-}
-
 // ------------------------------------------------------------------ metrics
 template <class T>
 __global__ void k_metrics(const T *__restrict__ a, const T *__restrict__ b, size_t pitch_elems, int H, int W, double *acc)

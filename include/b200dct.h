@@ -209,11 +209,37 @@ int b200dct_roundtrip_metrics(const b200dct_plan *plan,
  * (cudaMalloc, H2D, dct, idct, D2H: main_newAppr.cu:88-124), as one call on the current
  * device.  h_in/h_out are HOST pointers (pinned or pageable), tightly packed rows.
  * Internally the image is cut into block-row chunks that are copied, transformed and
- * copied back on rotating streams so H2D, kernel and D2H overlap.  Synchronous. */
+ * copied back on rotating streams so H2D, kernel and D2H overlap.  Synchronous.  The calling
+ * thread keeps one pipeline (4 streams, 8 chunk buffers) per device until it exits or calls
+ * b200dct_host_release(). */
 int b200dct_roundtrip_host(const b200dct_plan *plan,
                            const void *h_in, b200dct_dtype in_dt,
                            void *h_out, b200dct_dtype out_dt,
                            int H, int W);
+int b200dct_host_release(void);
+int b200dct_host_last_launch_count(void); /* kernels launched by this thread's last b200dct_roundtrip_host */
+
+/* The same pipeline as an object, for callers that process a SEQUENCE of images (the reference
+ * programs handle one image per process, main_newAppr.cu:26-165; a service handles many):
+ * b200dct_host_pipeline_submit only enqueues the image's chunks and returns, so consecutive images
+ * overlap -- image i+1 is uploading while image i is still coming back -- and the per-image
+ * fill/drain bubble of the synchronous call disappears.  h_in must stay valid and h_out must not
+ * be read until b200dct_host_pipeline_wait(ticket) (or _drain) returns; pinned host memory is
+ * needed for the copies to be asynchronous (pageable memory works, submit then blocks).
+ * A pipeline belongs to the device that was current at creation and to one submitting thread at a
+ * time.  chunk_bytes = 0: default (16 MiB, env B200DCT_HOST_CHUNK_MB); slots = 0: default (4).
+ * A chunk must hold at least one block-row (8 * W * element size), else B200DCT_ERR_SHAPE. */
+typedef struct b200dct_host_pipeline b200dct_host_pipeline;
+int  b200dct_host_pipeline_create(b200dct_host_pipeline **out, size_t chunk_bytes, int slots);
+void b200dct_host_pipeline_destroy(b200dct_host_pipeline *pipe);   /* waits for what is in flight */
+size_t b200dct_host_pipeline_chunk_bytes(const b200dct_host_pipeline *pipe);
+int  b200dct_host_pipeline_submit(b200dct_host_pipeline *pipe, const b200dct_plan *plan,
+                                  const void *h_in, b200dct_dtype in_dt,
+                                  void *h_out, b200dct_dtype out_dt,
+                                  int H, int W, unsigned long long *ticket_or_null);
+int  b200dct_host_pipeline_wait(b200dct_host_pipeline *pipe, unsigned long long ticket);
+int  b200dct_host_pipeline_drain(b200dct_host_pipeline *pipe);
+int  b200dct_host_pipeline_last_launch_count(const b200dct_host_pipeline *pipe);
 
 /* Sum of squared error and signal energy between two device images (same dtype,
  * F32 or U8), accumulated in double: MSE = sse/N, PEEN% = 100*sqrt(sse/energy)

@@ -503,3 +503,41 @@ def test_full_size_masks_and_streams(dct, oracle):
     order = torch.tensor(oracle.zigzag_i16(np.arange(64, dtype=np.float32).reshape(8, 8))[0, 0].astype(np.int64), device="cuda")
     assert torch.equal(zz, blocks[:, :, order])
     assert torch.equal(dct.inverse(zz, zigzag=True).view(torch.int32), dct.inverse(full).view(torch.int32))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8])
+def test_host_pipeline_overlapping_images(dct, oracle, dtype):
+    """b200dct_host_pipeline_*: several images in flight at once (pinned buffers, different
+    sizes, chunk boundaries inside and across images), each bit-exact against the oracle; tickets
+    complete individually."""
+    shapes = [(1024, 2048), (8, 64), (2056, 1024), (512, 4096), (1024, 2048)]
+    imgs = [(oracle.rand_image(h, w, 10 + i) if dtype == np.float32 else oracle.rand_image_u8(h, w, 10 + i))
+            for i, (h, w) in enumerate(shapes)]
+    want = [oracle.roundtrip(x) for x in imgs]
+    want = [w if dtype == np.float32 else oracle.to_u8(w) for w in want]
+    h_in = [torch.from_numpy(x).pin_memory() for x in imgs]
+    h_out = [torch.empty_like(x).pin_memory() for x in h_in]
+    with dct.HostPipeline(chunk_bytes=1 << 20, slots=3) as pipe:     # small chunks: many per image
+        assert pipe.chunk_bytes == 1 << 20
+        tickets = [pipe.submit(a, b) for a, b in zip(h_in, h_out)]
+        assert tickets == list(range(len(shapes)))
+        pipe.wait(tickets[1])
+        assert np.array_equal(h_out[0].numpy(), want[0]) and np.array_equal(h_out[1].numpy(), want[1])
+        with pytest.raises(dct.B200DCTError):
+            pipe.wait(99)                                            # not submitted yet
+        with pytest.raises(dct.B200DCTError):
+            pipe.submit(torch.zeros(8, 1 << 20), torch.zeros(8, 1 << 20))   # one block-row exceeds a chunk
+        pipe.drain()
+        for got, w in zip(h_out, want):
+            assert np.array_equal(got.numpy(), w)
+        # pageable host memory works too (the copies are then synchronous)
+        out = np.empty_like(imgs[2])
+        t = pipe.submit(imgs[2], out)
+        pipe.wait(t)
+        assert np.array_equal(out, want[2])
+    # the synchronous one-call form still works and can release its per-thread pipeline
+    got = dct.roundtrip_host(imgs[0])
+    assert np.array_equal(got, want[0])
+    assert dct.lib().b200dct_host_release() == 0
+    got = dct.roundtrip_host(imgs[3])
+    assert np.array_equal(got, want[3])
