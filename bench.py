@@ -417,26 +417,33 @@ def e2e_leg(m, plan, dev, world, args):
     for name, dtype, es in (("f32", torch.float32, 4), ("u8", torch.uint8, 1)):
         h_in = torch.randint(0, 256, (N_SIDE, N_SIDE), dtype=torch.int32).to(dtype).pin_memory()
         h_outs = [torch.empty(N_SIDE, N_SIDE, dtype=dtype).pin_memory() for _ in range(2)]
+        # the pipeline is a long-lived object of the caller (streams + chunk buffers): created and
+        # warmed up before the timed region, closed after it
+        pipe = m.HostPipeline(plan=plan)
         for i in range(2):
-            m.roundtrip_host(h_in, h_outs[i % 2], plan=plan)
+            pipe.submit(h_in, h_outs[i % 2])
+        pipe.drain()
         m.dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if hasattr(m, "HostPipeline"):
-            # consecutive images overlap: image i+1 is being uploaded while image i is still on its way back
-            with m.HostPipeline(plan=plan) as pipe:
-                for i in range(e2e_steps):
-                    pipe.submit(h_in, h_outs[i % 2])
-            api = "b200dct_host_pipeline_* (pinned host in/out, chunked H2D/kernel/D2H pipeline, consecutive images overlap)"
-        else:
-            for i in range(e2e_steps):
-                m.roundtrip_host(h_in, h_outs[i % 2], plan=plan)     # synchronous: returns with h_out complete
-            api = "b200dct_roundtrip_host (pinned host in/out, chunked H2D/kernel/D2H pipeline)"
+        # consecutive images overlap: image i+1 is being uploaded while image i is still on its way back
+        for i in range(e2e_steps):
+            pipe.submit(h_in, h_outs[i % 2])
+        pipe.drain()                                     # every h_out complete in host memory
+        api = ("b200dct_host_pipeline_submit/_drain (pinned host in/out, chunked H2D/kernel/D2H pipeline, "
+               f"{pipe.chunk_bytes >> 20} MiB chunks, consecutive images overlap)")
         torch.cuda.synchronize()
         local = time.perf_counter() - t0
         m.dist.barrier()
         secs = m.dist.max_over_ranks(local, dev)
-        res[name] = {"value": px * world * e2e_steps / secs / 1e9, "unit": UNIT, "h2d_bytes_per_step": px * es * world,
+        pipe.close()
+        # latency of ONE image through the synchronous one-call form (pays a fill/drain bubble per call)
+        m.roundtrip_host(h_in, h_outs[0], plan=plan)
+        t1 = time.perf_counter()
+        for i in range(3):
+            m.roundtrip_host(h_in, h_outs[i % 2], plan=plan)
+        sync_ms = (time.perf_counter() - t1) / 3 * 1e3
+        res[name] = {"single_image_sync_call_ms": sync_ms, "value": px * world * e2e_steps / secs / 1e9, "unit": UNIT, "h2d_bytes_per_step": px * es * world,
                      "d2h_bytes_per_step": px * es * world, "steps": e2e_steps, "ms_per_step": secs / e2e_steps * 1e3,
                      "api": api, "host_gb_s_each_way": px * es * world * e2e_steps / secs / 1e9}
         del h_in, h_outs

@@ -50,22 +50,29 @@ static void pipeline_free(b200dct_host_pipeline *p)
     (void)cudaGetLastError();
 }
 
-static size_t default_chunk_bytes()
+// Chunk sizes, measured on B200 / PCIe Gen5 (H2D alone 55.5 GB/s, D2H alone 56.3, both at once
+// 48.7 each way; profiles/r02_e2e_pipeline.txt, 8192^2 f32 = 256 MiB each way per image):
+//  * one image per call (synchronous form): every call pays one chunk of fill and one of drain, so
+//    chunks must be small -- 16 MiB x 4 slots: 6.16 ms (2..32 MiB tried in round 1);
+//  * a sequence of images through a pipeline object: no per-image bubble, so large chunks win --
+//    4 MiB 7.2 ms, 8: 6.4, 16: 5.89, 32: 5.65, 64 MiB x 3 slots: 5.55 ms = 48.4 GB/s each way =
+//    0.99 of the duplex ceiling (u8 images: 1.44 ms).
+static size_t env_mb(const char *name, int dflt)
 {
-    // ~16 MiB chunks (env B200DCT_HOST_CHUNK_MB; best of 2..32 MiB on B200).  PCIe Gen5 on the box:
-    // H2D alone 55.5 GB/s, D2H alone 57.2, both at once 49.8 each (profiles/r01_pcie.txt).
-    const char *e = getenv("B200DCT_HOST_CHUNK_MB");
-    const int mb = (e && atoi(e) >= 1 && atoi(e) <= 1024) ? atoi(e) : 16;
+    const char *e = getenv(name);
+    const int mb = (e && atoi(e) >= 1 && atoi(e) <= 1024) ? atoi(e) : dflt;
     return (size_t)mb << 20;
 }
+static size_t default_chunk_bytes() { return env_mb("B200DCT_HOST_CHUNK_MB", 16); }      // synchronous call
+static size_t default_pipeline_chunk_bytes() { return env_mb("B200DCT_PIPE_CHUNK_MB", 64); } // pipeline objects
 
 extern "C" int b200dct_host_pipeline_create(b200dct_host_pipeline **out, size_t chunk_bytes, int slots)
 {
     if (!out) return B200DCT_ERR_ARG;
     *out = nullptr;
-    if (slots == 0) slots = 4;
+    if (slots == 0) slots = 3;
     if (slots < 2 || slots > MAX_SLOTS) return B200DCT_ERR_ARG;
-    if (chunk_bytes == 0) chunk_bytes = default_chunk_bytes();
+    if (chunk_bytes == 0) chunk_bytes = default_pipeline_chunk_bytes();
     chunk_bytes = (chunk_bytes + 255) & ~(size_t)255;
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return B200DCT_ERR_NODEVICE;

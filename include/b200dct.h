@@ -227,7 +227,8 @@ int b200dct_host_last_launch_count(void); /* kernels launched by this thread's l
  * be read until b200dct_host_pipeline_wait(ticket) (or _drain) returns; pinned host memory is
  * needed for the copies to be asynchronous (pageable memory works, submit then blocks).
  * A pipeline belongs to the device that was current at creation and to one submitting thread at a
- * time.  chunk_bytes = 0: default (16 MiB, env B200DCT_HOST_CHUNK_MB); slots = 0: default (4).
+ * time.  chunk_bytes = 0: default (64 MiB, env B200DCT_PIPE_CHUNK_MB); slots = 0: default (3);
+ * device memory held: 2 * slots * chunk_bytes.
  * A chunk must hold at least one block-row (8 * W * element size), else B200DCT_ERR_SHAPE. */
 typedef struct b200dct_host_pipeline b200dct_host_pipeline;
 int  b200dct_host_pipeline_create(b200dct_host_pipeline **out, size_t chunk_bytes, int slots);
