@@ -60,6 +60,14 @@ def lib() -> C.CDLL:
         i16p = np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS")
         L.oracle_zigzag_i16.argtypes = [f32p, C.c_int, C.c_int, i16p]
         L.oracle_unzigzag_i16.argtypes = [i16p, C.c_int, C.c_int, f32p]
+        L.oracle_jpeg_Q_chroma.restype = C.POINTER(C.c_float)
+        L.oracle_rgb_to_ycc.argtypes = [u8p, C.c_size_t, u8p, u8p, u8p]
+        L.oracle_ycc_to_rgb.argtypes = [u8p, u8p, u8p, C.c_size_t, u8p]
+        L.oracle_roundtrip_rgb.argtypes = [u8p, C.c_int, C.c_int, f32p, f32p, f32p, C.c_uint64, u8p, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_huffman_spec.argtypes = [C.c_int, C.c_int, u8p, u8p, C.POINTER(C.c_int)]
+        L.oracle_huffman_lengths.argtypes = [C.c_int, C.c_int, u8p]
+        L.oracle_coded_bits.restype = C.c_uint64
+        L.oracle_coded_bits.argtypes = [i16p, C.c_size_t, C.c_int]
         _lib = L
     return _lib
 
@@ -70,6 +78,76 @@ def haweel_T() -> np.ndarray:
 
 def jpeg_Q() -> np.ndarray:
     return np.ctypeslib.as_array(lib().oracle_jpeg_Q(), shape=(64,)).copy()
+
+
+def jpeg_Q_chroma() -> np.ndarray:
+    """ITU-T T.81 Annex K.2 chrominance table."""
+    return np.ctypeslib.as_array(lib().oracle_jpeg_Q_chroma(), shape=(64,)).copy()
+
+
+def rgb_to_ycc(rgb: np.ndarray):
+    """libjpeg's jccolor.c conversion: interleaved (H, W, 3) u8 -> three (H, W) u8 planes."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    H, W = rgb.shape[:2]
+    y, cb, cr = (np.empty((H, W), np.uint8) for _ in range(3))
+    lib().oracle_rgb_to_ycc(rgb.reshape(-1), H * W, y.reshape(-1), cb.reshape(-1), cr.reshape(-1))
+    return y, cb, cr
+
+
+def ycc_to_rgb(y, cb, cr) -> np.ndarray:
+    """libjpeg's jdcolor.c conversion: three (H, W) u8 planes -> interleaved (H, W, 3) u8."""
+    H, W = y.shape
+    rgb = np.empty((H, W, 3), np.uint8)
+    lib().oracle_ycc_to_rgb(np.ascontiguousarray(y).reshape(-1), np.ascontiguousarray(cb).reshape(-1),
+                            np.ascontiguousarray(cr).reshape(-1), H * W, rgb.reshape(-1))
+    return rgb
+
+
+def roundtrip_rgb(rgb: np.ndarray, T=None, Q=None, Qc=None, keep: int = ALL_COEFFS, want_planes: bool = False,
+                  want_coef: bool = False, threads: int = 1):
+    """Interleaved RGB u8 -> YCbCr (libjpeg) -> per-plane reference round trip (Q for Y, Qc for
+    Cb/Cr) -> RGB u8.  Optionally also the (3, H, W) u8 planes after the round trip and the
+    (3, H, W) f32 coefficient planes."""
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    H, W = rgb.shape[:2]
+    T, Q = _tq(T, Q)
+    Qc = jpeg_Q_chroma() if Qc is None else np.ascontiguousarray(Qc, np.float32).reshape(64)
+    out = np.empty_like(rgb)
+    planes = np.empty((3, H, W), np.uint8) if want_planes else None
+    coef = np.empty((3, H, W), np.float32) if want_coef else None
+    lib().oracle_roundtrip_rgb(rgb.reshape(-1), H, W, T, Q, Qc, keep, out.reshape(-1),
+                               planes.ctypes.data if want_planes else None, coef.ctypes.data if want_coef else None, threads)
+    res = (out,)
+    if want_planes:
+        res += (planes,)
+    if want_coef:
+        res += (coef,)
+    return res[0] if len(res) == 1 else res
+
+
+def huffman_spec(which: int, table: int):
+    """(BITS[16], HUFFVAL) of the Annex K.3 table as a DHT marker carries it; which 0 DC / 1 AC."""
+    bits, vals, n = np.zeros(16, np.uint8), np.zeros(256, np.uint8), C.c_int()
+    lib().oracle_huffman_spec(which, table, bits, vals, C.byref(n))
+    return bits, vals[: n.value].copy()
+
+
+def huffman_lengths(which: int, table: int) -> np.ndarray:
+    out = np.zeros(256, np.uint8)
+    lib().oracle_huffman_lengths(which, table, out)
+    return out
+
+
+def coded_bits(stream: np.ndarray, table: int = 0) -> int:
+    """Baseline-JPEG entropy-coded size in bits of one plane's zig-zag int16 stream (.., 64)."""
+    stream = np.ascontiguousarray(stream, np.int16)
+    return int(lib().oracle_coded_bits(stream.reshape(-1), stream.size // 64, table))
+
+
+def compression_factor(coef: np.ndarray, table: int = 0) -> float:
+    """8*H*W / coded_bits of a coefficient plane (README.md:62-69 'Compr. Factor', see dct_oracle.c)."""
+    H, W = coef.shape
+    return 8.0 * H * W / coded_bits(zigzag_i16(coef), table)
 
 
 def dct2_T() -> np.ndarray:
