@@ -69,6 +69,10 @@ def lib() -> C.CDLL:
         L.b200dct_roundtrip_metrics.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp, vp, sz, vp]
         L.b200dct_roundtrip_any.argtypes = [vp, vp, i, sz, vp, sz, i, i, vp]
         L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
+        L.b200dct_plan_set_chroma_quant.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b200dct_plan_get_chroma_quant.argtypes = [vp, C.POINTER(C.c_float)]
+        L.b200dct_roundtrip_rgb.argtypes = [vp, vp, sz, vp, sz, vp, sz, i, i, vp]
+        L.b200dct_zigzag_coded_bits.argtypes = [vp, sz, i, i, i, vp, vp]
         L.b200dct_host_pipeline_create.argtypes = [C.POINTER(vp), sz, i]
         L.b200dct_host_pipeline_destroy.argtypes = [vp]
         L.b200dct_host_pipeline_destroy.restype = None
@@ -125,13 +129,15 @@ class Plan:
     """T, Q and the retained-coefficient mask (b200dct_plan)."""
 
     def __init__(self, T=None, Q=None, keep: int = ALL_COEFFS, path: int = PATH_AUTO, inverse: int = INVERSE_AUTO,
-                 dense: int = DENSE_AUTO):
+                 dense: int = DENSE_AUTO, Qc=None):
         self._h = C.c_void_p()
         _check(lib().b200dct_plan_create(C.byref(self._h)))
         if T is not None:
             self.set_transform(T)
         if Q is not None:
             self.set_quant(Q)
+        if Qc is not None:
+            self.set_chroma_quant(Qc)
         if keep != ALL_COEFFS:
             self.set_keep_mask(keep)
         if path != PATH_AUTO:
@@ -150,6 +156,15 @@ class Plan:
     def quant(self) -> np.ndarray:
         q = (C.c_float * 64)()
         _check(lib().b200dct_plan_get_quant(self._h, q))
+        return np.array(q[:], np.float32)
+
+    def set_chroma_quant(self, Q) -> None:
+        """Quantisation table of the Cb / Cr planes of roundtrip_rgb (default: T.81 Annex K.2)."""
+        _check(lib().b200dct_plan_set_chroma_quant(self._h, _f64(Q)))
+
+    def chroma_quant(self) -> np.ndarray:
+        q = (C.c_float * 64)()
+        _check(lib().b200dct_plan_get_chroma_quant(self._h, q))
         return np.array(q[:], np.float32)
 
     def set_keep_mask(self, mask: int) -> None:
@@ -362,9 +377,60 @@ def roundtrip_any(img, out=None, plan: Plan | None = None, stream=None):
     return out
 
 
-def roundtrip_with_metrics(img, out=None, coef=None, plan: Plan | None = None, stream=None):
+def roundtrip_rgb(rgb, out=None, streams=None, plan: Plan | None = None, stream=None):
+    """Colour round trip in one pass (b200dct_roundtrip_rgb): `rgb` is an (H, W, 3) uint8 CUDA
+    tensor (interleaved, as the reference's loader returns colour files); RGB -> YCbCr (libjpeg)
+    -> per-plane DCT / quantise (luminance table for Y, chrominance table for Cb, Cr) / IDCT ->
+    RGB.  `streams`: optional (3, H/8, W/8, 64) int16 tensor receiving the zig-zag coefficient
+    streams of Y, Cb, Cr."""
+    import torch
+
+    if not (rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.dim() == 3 and rgb.shape[2] == 3
+            and rgb.stride(2) == 1 and rgb.stride(1) == 3):
+        raise B200DCTError("expected an interleaved (H, W, 3) uint8 CUDA tensor")
+    H, W = int(rgb.shape[0]), int(rgb.shape[1])
+    with _on(rgb, stream):
+        if out is None:
+            out = torch.empty_like(rgb)
+        if not (out.is_cuda and out.dtype == torch.uint8 and tuple(out.shape) == (H, W, 3) and out.stride(2) == 1 and out.stride(1) == 3):
+            raise B200DCTError("out must be an interleaved (H, W, 3) uint8 CUDA tensor like rgb")
+        zp, zplane = None, 0
+        if streams is not None:
+            if not (streams.is_cuda and streams.dtype == torch.int16 and tuple(streams.shape) == (3, H // 8, W // 8, 64)
+                    and streams[0].is_contiguous()):
+                raise B200DCTError("streams must be a (3, H/8, W/8, 64) int16 CUDA tensor")
+            zp, zplane = streams.data_ptr(), streams.stride(0) * 2
+        _check(lib().b200dct_roundtrip_rgb(_plan(plan)._h, rgb.data_ptr(), rgb.stride(0), out.data_ptr(), out.stride(0),
+                                           zp, zplane, H, W, _stream(stream)))
+    return out
+
+
+def coded_bits(zz, table: int = 0, stream=None) -> int:
+    """Baseline-JPEG entropy-coded size in bits of one plane's zig-zag stream, an (H/8, W/8, 64)
+    int16 CUDA tensor (b200dct_zigzag_coded_bits); table 0 = luminance codes, 1 = chrominance."""
+    import torch
+
+    p, _, pitch, H, W = _zz_plane(zz)
+    with _on(zz, stream):
+        acc = torch.zeros(1, dtype=torch.int64, device=zz.device)
+        _check(lib().b200dct_zigzag_coded_bits(p, pitch, H, W, int(table), acc.data_ptr(), _stream(stream)))
+        return int(acc.item())
+
+
+def compression_factor(zz, table: int = 0, stream=None) -> float:
+    """8*H*W / coded_bits: the README's 'Compr. Factor' (README.md:62-69) under the baseline-JPEG
+    entropy coder.  `zz`: one plane's stream, or a (3, ...) stack (Y with the luminance codes,
+    Cb and Cr with the chrominance codes; CF of the whole colour image)."""
+    if zz.dim() == 4:
+        bits = sum(coded_bits(zz[c], 0 if c == 0 else 1, stream) for c in range(zz.shape[0]))
+        return 8.0 * zz.shape[0] * zz.shape[1] * zz.shape[2] * 64 / bits
+    return 8.0 * zz.shape[0] * zz.shape[1] * 64 / coded_bits(zz, table, stream)
+
+
+def roundtrip_with_metrics(img, out=None, coef=None, plan: Plan | None = None, stream=None, zigzag=False):
     """Fused round trip that also returns (MSE, PEEN%, non-zero coefficient count) of the
-    pass, computed inside the kernel (b200dct_roundtrip_metrics)."""
+    pass, computed inside the kernel (b200dct_roundtrip_metrics).  zigzag=True: `coef` is the
+    block-major int16 zig-zag stream."""
     import torch
 
     ip, idt, ipitch, H, W = _plane(img)
@@ -372,7 +438,10 @@ def roundtrip_with_metrics(img, out=None, coef=None, plan: Plan | None = None, s
         if out is None:
             out = torch.empty_like(img)
         op, odt, opitch = _same_plane(out, H, W, "out", (img.dtype,))
-        cp, cdt, cpitch = (None, F32, 0) if coef is None else _same_plane(coef, H, W, "coef", (torch.float32, torch.int16))
+        if coef is None:
+            cp, cdt, cpitch = None, F32, 0
+        else:
+            cp, cdt, cpitch = _zz_same(coef, H, W, "coef") if zigzag else _same_plane(coef, H, W, "coef", (torch.float32, torch.int16))
         nbytes = int(lib().b200dct_metrics_workspace_bytes(H, W))
         ws = torch.empty(max(1, nbytes // 8), dtype=torch.float64, device=img.device)
         acc = torch.zeros(3, dtype=torch.float64, device=img.device)

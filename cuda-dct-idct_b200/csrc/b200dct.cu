@@ -13,7 +13,7 @@
 #include <mutex>
 #include <new>
 
-#include "dct_kernels.cuh"
+#include "rgb_kernels.cuh"
 
 namespace b200dct {
 // one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
@@ -88,29 +88,25 @@ static cudaError_t reduce_partials_sparse(const double *partials, size_t n, doub
     return cudaGetLastError();
 }
 
-struct b200dct_plan {
-    float T[64];
-    float Q[64];
-    uint64_t mask;
-    bool sparse;     // T is bit-identical to Haweel's matrix
-    bool q_default;  // Q is the JPEG luminance table
-    bool q_fastdiv;  // every divisor is in the exhaustively proven set (integers 1..255)
-    int path;        // b200dct_path
-    int inverse;     // b200dct_inverse_mode
-    int dense;       // b200dct_dense_mode
-    bool symmetric;  // dense T whose even rows are symmetric and odd rows antisymmetric
-    int tk;          // TK_HAWEEL / TK_DENSE_SYM / TK_DENSE: the kernels this plan runs
-    CommonParams cp; // device-ready tables
-};
+#include "plan_internal.h"
 
 static thread_local int tl_launches = 0;
 static thread_local const char *tl_path = "none";
+namespace b200dct {
+void note_launch(int launches, const char *path)
+{
+    tl_launches = launches;
+    tl_path = path;
+}
+} // namespace b200dct
 
 static void plan_refresh(b200dct_plan *pl)
 {
     pl->sparse = true;
     pl->q_default = true;
     pl->q_fastdiv = true;
+    pl->qc_default = true;
+    pl->qc_fastdiv = true;
     for (int k = 0; k < 64; k++) {
         const float h = haweel(k / 8, k % 8);
         if (memcmp(&h, &pl->T[k], 4) != 0 && !(h == 0.0f && pl->T[k] == 0.0f)) pl->sparse = false;
@@ -121,6 +117,13 @@ static void plan_refresh(b200dct_plan *pl)
         pl->cp.q.neg_d[k] = -d;
         pl->cp.q.rcp[k] = 1.0f / d; // IEEE RN on the host
         pl->cp.q.keep[k] = ((pl->mask >> k) & 1) ? 0xffffffffu : 0u;
+        const float dc = pl->Qc[k];
+        if (dc != jpeg_q_chroma(k)) pl->qc_default = false;
+        if (!(dc >= 1.0f && dc <= 255.0f && dc == floorf(dc))) pl->qc_fastdiv = false;
+        pl->qc.d[k] = dc;
+        pl->qc.neg_d[k] = -dc;
+        pl->qc.rcp[k] = 1.0f / dc;
+        pl->qc.keep[k] = pl->cp.q.keep[k];
         pl->cp.t.t[k] = pl->T[k];
         pl->cp.t.tt[(k % 8) * 8 + k / 8] = pl->T[k];
     }
@@ -153,6 +156,7 @@ extern "C" int b200dct_plan_create(b200dct_plan **out)
     for (int k = 0; k < 64; k++) {
         pl->T[k] = haweel(k / 8, k % 8);
         pl->Q[k] = jpeg_q(k);
+        pl->Qc[k] = jpeg_q_chroma(k);
     }
     pl->mask = ~(uint64_t)0;
     pl->path = B200DCT_PATH_AUTO;
@@ -190,6 +194,23 @@ extern "C" int b200dct_plan_get_quant(const b200dct_plan *pl, float *q)
 {
     if (!pl || !q) return B200DCT_ERR_ARG;
     memcpy(q, pl->Q, sizeof(pl->Q));
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_set_chroma_quant(b200dct_plan *pl, const float *q)
+{
+    if (!pl || !q) return B200DCT_ERR_ARG;
+    for (int k = 0; k < 64; k++)
+        if (!isfinite(q[k]) || q[k] == 0.0f) return B200DCT_ERR_QUANT;
+    memcpy(pl->Qc, q, sizeof(pl->Qc));
+    plan_refresh(pl);
+    return B200DCT_OK;
+}
+
+extern "C" int b200dct_plan_get_chroma_quant(const b200dct_plan *pl, float *q)
+{
+    if (!pl || !q) return B200DCT_ERR_ARG;
+    memcpy(q, pl->Qc, sizeof(pl->Qc));
     return B200DCT_OK;
 }
 
@@ -433,6 +454,15 @@ static bool pdl_for(bool capturing)
     }
     return use_pdl() && (!capturing || cap == 1);
 }
+namespace b200dct {
+bool use_factored_inverse_u8(const b200dct_plan *pl) { return use_factored_inverse(pl, MODE_RT, DT_U8); }
+bool pdl_enabled(cudaStream_t s)
+{
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+    return pdl_for(capturing);
+}
+} // namespace b200dct
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
 static bool compiled_masks() // env B200DCT_COMPILED_MASKS=0: retained-coefficient masks as runtime data only (A/B)
 {

@@ -1,0 +1,29 @@
+// plan_internal.h -- the plan object behind the opaque b200dct_plan handle (host TUs only).
+#pragma once
+#include "b200dct.h"
+#include "rgb_kernels.cuh"
+
+struct b200dct_plan {
+    float T[64];
+    float Q[64];
+    float Qc[64];    // chrominance table of the colour entry point (default: ITU-T T.81 Annex K.2)
+    uint64_t mask;
+    bool sparse;     // T is bit-identical to Haweel's matrix
+    bool q_default;  // Q is the JPEG luminance table
+    bool q_fastdiv;  // every divisor is in the exhaustively proven set (integers 1..255)
+    int path;        // b200dct_path
+    int inverse;     // b200dct_inverse_mode
+    int dense;       // b200dct_dense_mode
+    bool symmetric;  // dense T whose even rows are symmetric and odd rows antisymmetric
+    int tk;          // TK_HAWEEL / TK_DENSE_SYM / TK_DENSE: the kernels this plan runs
+    b200dct::CommonParams cp; // device-ready tables
+    b200dct::QuantTables qc; // device-ready chrominance tables (same mask)
+    bool qc_default, qc_fastdiv;
+};
+
+
+namespace b200dct {
+void note_launch(int launches, const char *path); // b200dct_last_launch_count / b200dct_last_path of this thread
+bool use_factored_inverse_u8(const b200dct_plan *pl);
+bool pdl_enabled(cudaStream_t s);
+}

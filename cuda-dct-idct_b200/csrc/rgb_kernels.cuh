@@ -1,0 +1,173 @@
+// rgb_kernels.cuh -- interleaved RGB u8 -> YCbCr -> per-plane fused round trip -> RGB u8, ONE pass.
+//
+// SURVEY.md section 8f "generality: multi-channel / YCbCr with the chroma Q table".  The reference's
+// loader returns interleaved RGB for colour files (utils.cu:62-64) and its programs then ignore the
+// channel count (main_newAppr.cu:47).  This kernel is the colour version of the same pipeline:
+//   RGB -> YCbCr  : libjpeg's jccolor.c fixed point (SCALEBITS 16, FIX(x) = x*65536+0.5, ONE_HALF
+//                   rounding, CBCR_OFFSET + ONE_HALF - 1 for Cb/Cr), 8-bit samples, 4:4:4
+//   per plane     : the reference's u8 pipeline (convertToFloat utils.cu:10-15 -> dct_all_blocks_cuda
+//                   -> idct_all_blocks_cuda -> convertToUnsignedChar utils.cu:18-24), luminance
+//                   table for Y, ITU-T T.81 Annex K.2 chrominance table for Cb and Cr
+//   YCbCr -> RGB  : libjpeg's jdcolor.c (Cr_r_tab / Cb_b_tab rounded per entry, the two green terms
+//                   share one shift).
+// One thread owns one 8x8 pixel position in all three planes.  The input is read once (three
+// 8-byte loads per row and lane; a warp's row is one contiguous 768-byte span), Y goes straight
+// into the transform registers, Cb and Cr wait as bytes in shared memory; every finished plane is
+// parked as bytes in shared memory until the last one is done, then the rows are converted back
+// and stored.  24 KiB of shared memory per 128-thread CTA, no barrier (every thread only ever
+// touches its own slots).
+//
+// The fixed-point colour arithmetic runs on the FP32 pipe, exactly: every product and partial sum
+// of the libjpeg expressions is an integer of magnitude < 2^24 (e.g. 255 * 65536 + 32768), the
+// coefficients are pre-scaled by 2^-16 (a pure exponent shift), so each FMA is exact and
+// ">> 16" (arithmetic) is a round-toward-minus-infinity to integer, done by adding 1.5 * 2^23 in
+// RM mode.  Bit-identical to the integer code (tests/test_gpu_rgb.py against the CPU restatement, which is
+// pinned against the real libjpeg).
+#pragma once
+
+#include "dct_kernels.cuh"
+
+namespace b200dct {
+
+// ITU-T T.81 Annex K.2
+__host__ __device__ constexpr float jpeg_q_chroma(int k)
+{
+    constexpr float q[64] = {
+        17, 18, 24, 47, 99, 99, 99, 99,
+        18, 21, 26, 66, 99, 99, 99, 99,
+        24, 26, 56, 99, 99, 99, 99, 99,
+        47, 66, 99, 99, 99, 99, 99, 99,
+        99, 99, 99, 99, 99, 99, 99, 99,
+        99, 99, 99, 99, 99, 99, 99, 99,
+        99, 99, 99, 99, 99, 99, 99, 99,
+        99, 99, 99, 99, 99, 99, 99, 99};
+    return q[k];
+}
+struct QImmChroma {
+    static constexpr bool masked = false;
+    static constexpr bool fastdiv = true;
+    __device__ __forceinline__ float neg_d(int k) const { return -jpeg_q_chroma(k); }
+    __device__ __forceinline__ float rcp(int k) const { return 1.0f / jpeg_q_chroma(k); }
+    __device__ __forceinline__ float d(int k) const { return jpeg_q_chroma(k); }
+    __device__ __forceinline__ uint32_t keep(int) const { return 0xffffffffu; }
+};
+
+struct RgbParams {
+    const void *in;  // interleaved RGB u8, 8-byte aligned rows
+    void *out;
+    void *zz;        // optional: three block-major zig-zag int16 streams (Y, Cb, Cr), zz_plane bytes apart
+    size_t in_pitch, out_pitch, zz_plane, zz_pitch; // bytes; zz_pitch = bytes per block-row of one stream
+    int bx, by;
+    QuantTables q;   // luminance
+    QuantTables qc;  // chrominance
+};
+
+constexpr float RGB_MAGIC = 12582912.0f; // 1.5 * 2^23: x + MAGIC in RM mode = MAGIC + floor(x) for |x| < 2^22
+#define B200_FIX(x) ((float)((int)((x) * 65536.0 + 0.5)) * (1.0f / 65536.0f))
+
+__device__ __forceinline__ float floor_magic(float x) { return __fadd_rd(x, RGB_MAGIC); } // MAGIC + floor(x)
+
+// byte j (0..23) of a 24-byte row held in six 32-bit words, as float
+template <int J>
+__device__ __forceinline__ float row_byte(const uint32_t (&w)[6])
+{
+    return u8_to_float(w[J >> 2], J & 3);
+}
+
+// QK: 0 immediates (default tables, all coefficients kept), 1 parameter tables + exact fast division + mask,
+//     2 parameter tables + __fdiv_rn + mask
+template <int QK, bool FINV>
+__global__ void __launch_bounds__(128, 4) k_rgb(const __grid_constant__ RgbParams P)
+{
+    // [plane][row][thread] 8-byte slots: a warp's access is 256 contiguous bytes (conflict-free)
+    __shared__ uint2 park[3][8][128];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int bxi = blockIdx.y * 32 + threadIdx.x;
+    const long long by = (long long)blockIdx.x * 4 + threadIdx.y;
+    if (bxi >= P.bx || by >= P.by) return;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    float2 p[8][4];
+    // ---- load + RGB -> YCbCr (jccolor.c rgb_ycc_convert)
+    {
+        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 24;
+        sfor<8>([&](auto r) {
+            const uint2 *row = reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch);
+            const uint2 a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
+            const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+            float yv[8], cbv[8], crv[8];
+            sfor<8>([&](auto k) {
+                const float R = row_byte<3 * IC(k)>(w), G = row_byte<3 * IC(k) + 1>(w), B = row_byte<3 * IC(k) + 2>(w);
+                // every partial sum is an integer multiple of 2^-16 below 2^8: exact
+                const float y = __fmaf_rn(R, B200_FIX(0.29900), __fmaf_rn(G, B200_FIX(0.58700), __fmaf_rn(B, B200_FIX(0.11400), 0.5f)));
+                const float cb = __fmaf_rn(R, -B200_FIX(0.16874), __fmaf_rn(G, -B200_FIX(0.33126), __fmaf_rn(B, 0.5f, 128.0f + 32767.0f / 65536.0f)));
+                const float cr = __fmaf_rn(R, 0.5f, __fmaf_rn(G, -B200_FIX(0.41869), __fmaf_rn(B, -B200_FIX(0.08131), 128.0f + 32767.0f / 65536.0f)));
+                yv[IC(k)] = floor_magic(y) - (RGB_MAGIC + 128.0f); // sample - 128: the transform's input (sub_matrix_scalar)
+                cbv[IC(k)] = floor_magic(cb);                      // low mantissa byte = the sample
+                crv[IC(k)] = floor_magic(cr);
+            });
+            sfor<4>([&](auto j) { p[IC(r)][IC(j)] = make_float2(yv[2 * IC(j)], yv[2 * IC(j) + 1]); });
+            auto pack = [](const float (&v)[8]) {
+                uint2 o;
+                o.x = __byte_perm(__byte_perm(__float_as_uint(v[0]), __float_as_uint(v[1]), 0x0040), __byte_perm(__float_as_uint(v[2]), __float_as_uint(v[3]), 0x0040), 0x5410);
+                o.y = __byte_perm(__byte_perm(__float_as_uint(v[4]), __float_as_uint(v[5]), 0x0040), __byte_perm(__float_as_uint(v[6]), __float_as_uint(v[7]), 0x0040), 0x5410);
+                return o;
+            };
+            park[1][IC(r)][tid] = pack(cbv);
+            park[2][IC(r)][tid] = pack(crv);
+        });
+    }
+
+    auto emit = [&](int plane, float2 (&c)[8][4]) {
+        if (P.zz) st_block_zigzag((char *)P.zz + (size_t)plane * P.zz_plane + (size_t)by * P.zz_pitch + (size_t)bxi * 128, c);
+    };
+    auto round_trip = [&](auto chroma, int plane) {
+        constexpr bool CH = decltype(chroma)::value;
+        auto run = [&](const auto &qp) {
+            forward_block<KeepAll>(p, HaweelT<false, true>{}, qp);
+            emit(plane, p);
+            if constexpr (FINV) {
+                inverse_block_fast<true>(p, qp);
+            } else {
+                inverse_block<KeepAll>(p, HaweelT<true, true>{}, qp);
+                sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); }); // add_matrix_scalar, utils_kernels.cu:29
+            }
+        };
+        if constexpr (QK == 0) {
+            if constexpr (CH) run(QImmChroma{});
+            else run(QImm{});
+        } else {
+            run(QParam<true, QK == 1>(CH ? P.qc : P.q));
+        }
+        sfor<8>([&](auto r) { park[plane][IC(r)][tid] = pack_u8_row(p[IC(r)]); }); // convertToUnsignedChar, utils.cu:21
+    };
+
+    round_trip(std::false_type{}, 0);
+#pragma unroll 1
+    for (int plane = 1; plane < 3; plane++) { // Cb, Cr: same code, run twice
+        sfor<8>([&](auto r) { unpack_u8_shifted(park[plane][IC(r)][tid], p[IC(r)]); });
+        round_trip(std::true_type{}, plane);
+    }
+
+    // ---- YCbCr -> RGB (jdcolor.c ycc_rgb_convert) + store
+    char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 24;
+    sfor<8>([&](auto r) {
+        const uint2 yw = park[0][IC(r)][tid], bw = park[1][IC(r)][tid], rw = park[2][IC(r)][tid];
+        float o[24];
+        sfor<8>([&](auto k) {
+            const uint32_t ys = IC(k) < 4 ? yw.x : yw.y, bs = IC(k) < 4 ? bw.x : bw.y, rs = IC(k) < 4 ? rw.x : rw.y;
+            const float ym = u8_to_float(ys, IC(k) & 3) - RGB_MAGIC;
+            const float cb = u8_shifted(bs, IC(k) & 3), cr = u8_shifted(rs, IC(k) & 3);
+            o[3 * IC(k)] = floor_magic(__fmaf_rn(cr, B200_FIX(1.40200), 0.5f)) + ym;
+            o[3 * IC(k) + 1] = floor_magic(__fmaf_rn(cr, -B200_FIX(0.71414), __fmaf_rn(cb, -B200_FIX(0.34414), 0.5f))) + ym;
+            o[3 * IC(k) + 2] = floor_magic(__fmaf_rn(cb, B200_FIX(1.77200), 0.5f)) + ym;
+        });
+        uint2 *row = reinterpret_cast<uint2 *>(dst + IC(r) * P.out_pitch);
+        row[0] = make_uint2(pack4_u8(o[0], o[1], o[2], o[3]), pack4_u8(o[4], o[5], o[6], o[7]));       // range_limit = saturation
+        row[1] = make_uint2(pack4_u8(o[8], o[9], o[10], o[11]), pack4_u8(o[12], o[13], o[14], o[15]));
+        row[2] = make_uint2(pack4_u8(o[16], o[17], o[18], o[19]), pack4_u8(o[20], o[21], o[22], o[23]));
+    });
+}
+
+} // namespace b200dct

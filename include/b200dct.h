@@ -205,6 +205,35 @@ int b200dct_roundtrip_metrics(const b200dct_plan *plan,
                               int H, int W, double *d_acc3,
                               void *workspace, size_t workspace_bytes, void *stream);
 
+/* Colour images (multi-channel / YCbCr with the chroma Q table).  The
+ * reference's loader returns interleaved RGB for colour files (utils.cu:62-64: channels = 3) and
+ * its programs then ignore the channel count (main_newAppr.cu:47).  This is the colour version of
+ * the same fused pipeline, ONE pass over the image:
+ *   RGB -> YCbCr exactly as libjpeg (the reference's image library; jccolor.c: 16-bit fixed point,
+ *   8-bit samples, no subsampling), then per plane the reference's u8 pipeline (convertToFloat ->
+ *   dct -> quantise -> dequantise -> idct -> convertToUnsignedChar) with the plan's luminance table
+ *   for Y and its chrominance table (default ITU-T T.81 Annex K.2) for Cb and Cr, then YCbCr -> RGB
+ *   exactly as libjpeg's decoder (jdcolor.c).
+ * rgb/out: DEVICE pointers, H x W pixels of 3 bytes, 8-byte aligned rows (pitch in bytes, % 8 == 0).
+ * zz3_or_null: optionally the three block-major zig-zag int16 coefficient streams (Y, Cb, Cr;
+ * layout of B200DCT_I16_ZIGZAG), zz_plane_bytes apart (>= H*W*2, % 16 == 0).  The plan's mask
+ * applies to all three planes; its inverse mode as for 8-bit grey images (EXACT: planes
+ * bit-identical to the reference's arithmetic).  Haweel's T only (B200DCT_ERR_ARG otherwise). */
+int b200dct_plan_set_chroma_quant(b200dct_plan *plan, const float q[64]);
+int b200dct_plan_get_chroma_quant(const b200dct_plan *plan, float q[64]);
+int b200dct_roundtrip_rgb(const b200dct_plan *plan, const void *rgb, size_t in_pitch,
+                          void *out, size_t out_pitch, void *zz3_or_null, size_t zz_plane_bytes,
+                          int H, int W, void *stream);
+
+/* Size in BITS of the baseline-JPEG entropy-coded scan (ITU-T T.81 sequential Huffman with the
+ * Annex K.3 tables, i.e. what libjpeg writes with optimize off; no headers, stuffing or padding)
+ * of one plane's zig-zag stream (B200DCT_I16_ZIGZAG layout; pitch = bytes per block-row), ADDED
+ * to *d_bits (device, 8-byte aligned).  table: 0 luminance codes, 1 chrominance codes.  This
+ * defines the "Compr. Factor" of the reference's README (README.md:62-69), for which the
+ * reference has no code:  CF = 8 * H * W / bits. */
+int b200dct_zigzag_coded_bits(const void *zz, size_t pitch, int H, int W, int table,
+                              unsigned long long *d_bits, void *stream);
+
 /* Host-buffer round trip: what the reference's main() does around its two calls
  * (cudaMalloc, H2D, dct, idct, D2H: main_newAppr.cu:88-124), as one call on the current
  * device.  h_in/h_out are HOST pointers (pinned or pageable), tightly packed rows.
