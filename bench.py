@@ -506,6 +506,16 @@ def extras_single_gpu(m, dev, peak):
         ms = time_config(m, rotating(m, plan, ins8, outs8, stream))
         ex[key] = entry(ms, N * N, 2, what=what, kernel_path=m.api.last_path())
     del ins8, outs8
+    # colour: interleaved RGB u8 -> YCbCr -> three planes (luma / chroma tables) -> RGB, one pass (6 B/px)
+    rgb_in = [torch.randint(0, 256, (N, N, 3), device=dev, dtype=torch.uint8) for _ in range(2)]
+    rgb_out = [torch.empty_like(x) for x in rgb_in]
+    plan_rgb = m.Plan()
+
+    def rgb_step(i):
+        m.roundtrip_rgb(rgb_in[i % 2], out=rgb_out[i % 2], plan=plan_rgb, stream=stream)
+    ex["rgb_8192"] = entry(time_config(m, rgb_step), N * N, 6, what="b200dct_roundtrip_rgb: 8192^2 RGB pixels (3 planes) per pass, library default inverse",
+                           kernel_path=m.api.last_path())
+    del rgb_in, rgb_out
     # the drop-in two-call API (dct_all_blocks_cuda then idct_all_blocks_cuda), f32, 16 B/px
     a = [torch.randint(0, 256, (N, N), device=dev, dtype=torch.int32).float() for _ in range(2)]
     c = [torch.empty(N, N, device=dev) for _ in range(2)]

@@ -449,6 +449,85 @@ __global__ void __launch_bounds__(128, 5) k_any(const __grid_constant__ AnyParam
     });
 }
 
+// ---- 8-bit images of any size and alignment: no shared-memory stage at all.
+// Byte-aligned rows still consist of aligned 32-bit words: a lane fetches the three aligned words
+// that cover its block's 8-byte row and funnel-shifts its own 8 bytes out of them (3 LDG.32 + 2
+// SHF per row instead of 8 one-byte loads, conversions and a trip through shared memory), and on
+// the way out re-aligns with its left neighbour's last bytes (one SHFL + two SHF) so that almost
+// every store is an aligned 32-bit word; only the bytes at the two ends of a warp's 256-pixel span
+// and ragged blocks at the right image edge move as single bytes.  Bytes of neighbouring spans
+// that ride along in a loaded word are shifted out unused (so concurrent in-place updates of
+// them by other warps are harmless) and are never written.  Rows beyond the bottom edge and
+// pixels beyond the right edge replicate the last row / pixel (np.pad(mode="edge")).
+// 8191^2: 125 us with the staged kernel above -> see profiles/r02_any_size.txt.
+template <int TK, int QMODE, bool FINV>
+__global__ void __launch_bounds__(128, 5) k_any_u8(const __grid_constant__ AnyParams P)
+{
+    constexpr bool BIASED = inverse_is_biased(TK, FINV);
+    const int lane = threadIdx.x;
+    const long long y0 = ((long long)blockIdx.x * 4 + threadIdx.y) * 8;
+    if (y0 >= P.H) return; // warp-uniform
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int xb = blockIdx.y * 256 + lane * 8;       // first pixel of this lane's block
+    const bool full = xb + 8 <= P.W;                  // the whole block row lies inside the image
+    const bool partial = !full && xb < P.W;
+
+    float2 p[8][4];
+    sfor<8>([&](auto r) {
+        const long long y = y0 + IC(r) < P.H ? y0 + IC(r) : P.H - 1;
+        const uint8_t *row = (const uint8_t *)P.in + (size_t)y * P.in_pitch;
+        uint2 w = make_uint2(0u, 0u);
+        if (full) {
+            const uintptr_t a = (uintptr_t)(row + xb);
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            const unsigned sh = (unsigned)(a & 3) * 8;   // warp-uniform: xb is a multiple of 8
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = sh ? wp[2] : 0u; // the third word holds own bytes iff sh != 0
+            w.x = __funnelshift_r(w0, w1, sh);
+            w.y = __funnelshift_r(w1, w2, sh);
+        } else if (partial) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t b = row[xb + k < P.W ? xb + k : P.W - 1];
+                if (k < 4) w.x |= b << (8 * k);
+                else w.y |= b << (8 * (k - 4));
+            }
+        }
+        unpack_u8_shifted(w, p[IC(r)]);
+    });
+
+    run_block<MODE_RT, TK, QMODE, true, FINV>(p, P.cp, [](float2 (&)[8][4]) {});
+
+    const bool next_full = __shfl_down_sync(0xffffffffu, (int)full, 1) && lane < 31;
+    sfor<8>([&](auto r) {
+        const uint2 o = BIASED ? pack_u8_row(p[IC(r)]) : pack_u8_plus128(p[IC(r)]);
+        const uint32_t left_hi = __shfl_up_sync(0xffffffffu, o.y, 1); // the left neighbour's last four bytes
+        if (y0 + IC(r) < P.H) {                                        // warp-uniform
+            uint8_t *dst = (uint8_t *)P.out + (size_t)(y0 + IC(r)) * P.out_pitch + xb;
+            if (full) {
+                const unsigned so = (unsigned)((uintptr_t)dst & 3);   // warp-uniform
+                uint32_t *q = reinterpret_cast<uint32_t *>((uintptr_t)dst & ~(uintptr_t)3);
+                if (so == 0) {
+                    q[0] = o.x;
+                    q[1] = o.y;
+                } else {
+                    const unsigned s = so * 8;
+                    if (lane > 0) q[0] = __funnelshift_l(left_hi, o.x, s); // neighbour's last `so` bytes + my first 4-so
+                    else
+                        for (unsigned k = 0; k < 4 - so; k++) dst[k] = (uint8_t)(o.x >> (8 * k));
+                    q[1] = __funnelshift_l(o.x, o.y, s);
+                    if (!next_full) // nobody to my right completes my last word
+                        for (unsigned k = 0; k < so; k++) dst[8 - so + k] = (uint8_t)(o.y >> (8 * (4 - so + k)));
+                }
+            } else if (partial) {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (xb + k < P.W) dst[k] = (uint8_t)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
+            }
+        }
+    });
+}
+
 // ============================================================== TMA family
 // Tile = 8 image rows x 32 blocks (256 pixels).  Shared-memory images of a tile:
 //   f32 : 8 KiB, rows of 1 KiB = 8 segments of 128 B, hardware SWIZZLE_128B: the 16-byte

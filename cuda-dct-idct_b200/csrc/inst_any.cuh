@@ -19,7 +19,8 @@ static cudaError_t launch_one(const AnyParams &P, dim3 grid, dim3 block, cudaStr
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_any<TK, QM, PIX, FINV>, P);
+    if constexpr (PIX == DT_U8) return cudaLaunchKernelEx(&cfg, k_any_u8<TK, QM, FINV>, P); // word-packed, no shared-memory stage
+    else return cudaLaunchKernelEx(&cfg, k_any<TK, QM, PIX, FINV>, P);
 }
 
 template <int PIX>

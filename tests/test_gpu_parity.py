@@ -541,3 +541,34 @@ def test_host_pipeline_overlapping_images(dct, oracle, dtype):
     assert dct.lib().b200dct_host_release() == 0
     got = dct.roundtrip_host(imgs[3])
     assert np.array_equal(got, want[3])
+
+
+@pytest.mark.parametrize("W", [8, 13, 256, 523, 1031])
+def test_any_size_u8_every_alignment(dct, oracle, W):
+    """The word-packed 8-bit any-size kernel: every combination of source and destination byte
+    alignment (0..3), row pitches that change the alignment from row to row, widths that end inside
+    a word / inside a block / across several 256-pixel warp spans; frames keep their sentinels."""
+    H = 21
+    rng = np.random.default_rng(W)
+    img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    padded = np.pad(img, ((0, -H % 8), (0, -W % 8)), mode="edge")
+    want = oracle.roundtrip(np.ascontiguousarray(padded))[:H, :W]
+    for pitch_extra in (0, 1, 2, 7):
+        for so in range(4):
+            for do in range(4):
+                src = torch.full((H + 1, W + 8 + pitch_extra), 9, dtype=torch.uint8, device="cuda")
+                dst = torch.full((H + 1, W + 8 + pitch_extra), 77, dtype=torch.uint8, device="cuda")
+                src[:H, so:so + W] = dev(img)
+                dct.roundtrip_any(src[:H, so:so + W], out=dst[:H, do:do + W])
+                got = host(dst)
+                assert np.array_equal(got[:H, do:do + W], want), (pitch_extra, so, do)
+                got[:H, do:do + W] = 77
+                assert (got == 77).all(), ("sentinel", pitch_extra, so, do)
+        # in place on an unaligned view
+        buf = torch.full((H, W + 5 + pitch_extra), 5, dtype=torch.uint8, device="cuda")
+        buf[:, 3:3 + W] = dev(img)
+        dct.roundtrip_any(buf[:, 3:3 + W], out=buf[:, 3:3 + W])
+        got = host(buf)
+        assert np.array_equal(got[:, 3:3 + W], want)
+        got[:, 3:3 + W] = 5
+        assert (got == 5).all()
