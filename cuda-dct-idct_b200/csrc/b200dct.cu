@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 
+#include "any_kernels.cuh"
 #include "rgb_kernels.cuh"
 
 namespace b200dct {
@@ -80,6 +81,15 @@ static __global__ void __launch_bounds__(REDUCE_THREADS) k_reduce_partials(const
         __syncthreads();
     }
     if (threadIdx.x < 3) acc[threadIdx.x] += red[threadIdx.x][0];
+}
+
+// TMA-family metrics: the kernel leaves exact integer sums (2^-12 fixed point) in macc[0..2]
+static __global__ void k_finish_fixed_point(unsigned long long *macc, double *acc)
+{
+    if (threadIdx.x < 3) {
+        const double v = (double)(long long)macc[threadIdx.x];
+        acc[threadIdx.x] += threadIdx.x < 2 ? v / (double)METRICS_FIXED_POINT : v;
+    }
 }
 
 static cudaError_t reduce_partials_sparse(const double *partials, size_t n, double *acc, cudaStream_t s)
@@ -398,6 +408,7 @@ constexpr int SCHED_SLOTS = 4096;
 constexpr int CAPTURE_SLOTS = 4096;
 struct SchedRing {
     uint32_t *base[64] = {};
+    unsigned long long *macc[64] = {}; // one zeroed {sse, energy, nnz} integer triple per slot (metrics kernels)
     unsigned next[64] = {};
     unsigned next_capture[64] = {};
     std::mutex mu;
@@ -412,10 +423,12 @@ uint32_t *sched_slot(bool capturing)
     if (!g_sched.base[dev]) {
         if (capturing) return nullptr;
         uint32_t *p = nullptr;
-        const size_t bytes = (size_t)(SCHED_SLOTS + CAPTURE_SLOTS) * 2 * sizeof(uint32_t);
+        const size_t nslots = (size_t)(SCHED_SLOTS + CAPTURE_SLOTS);
+        const size_t bytes = nslots * 2 * sizeof(uint32_t) + nslots * 3 * sizeof(unsigned long long);
         if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
         if (cudaMemset(p, 0, bytes) != cudaSuccess) { cudaFree(p); return nullptr; }
         g_sched.base[dev] = p;
+        g_sched.macc[dev] = reinterpret_cast<unsigned long long *>(p + nslots * 2);
     }
     if (capturing) {
         if (g_sched.next_capture[dev] >= (unsigned)CAPTURE_SLOTS) return nullptr;
@@ -423,6 +436,13 @@ uint32_t *sched_slot(bool capturing)
     }
     const unsigned s = g_sched.next[dev]++ % SCHED_SLOTS;
     return g_sched.base[dev] + 2 * s;
+}
+// the integer accumulators that belong to a ticket-counter pair
+unsigned long long *sched_macc(const uint32_t *slot)
+{
+    int dev = -1;
+    if (!slot || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !g_sched.base[dev]) return nullptr;
+    return g_sched.macc[dev] + 3 * ((slot - g_sched.base[dev]) / 2);
 }
 } // namespace
 
@@ -505,7 +525,12 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // profiles/r01_small_sizes.txt): 256^2 3.4 vs 6.7 us, 2048^2 7.9 vs 9.7, 4096^2 22.9 vs 24.6,
     // 5120^2 34.9 vs 35.0, 6144^2 48.9 vs 48.0, 8192^2 83.8 vs 81.8.
     const bool big = (unsigned long long)H * (unsigned long long)W >= (28ull << 20);
-    const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big);
+    // Symmetric dense T (16+16 FMA/px): the direct family wins up to 12288^2 (84.6 vs 88.0 us at 8192^2,
+    // 187.7 vs 189.0 at 12288^2), the persistent TMA kernel beyond (16384^2: 321.9 vs 333.9 us;
+    // profiles/r02_dense_paths.txt).  Ordered-chain dense kernels stay on the direct family.
+    const bool huge = (unsigned long long)H * (unsigned long long)W >= (200ull << 20);
+    const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big) ||
+                            (bytes_per_px >= 4 && pl->tk == TK_DENSE_SYM && huge);
     // Under stream capture the launch takes a ticket-counter pair of its own (see SchedRing); when
     // none is left (or the pools do not exist yet) AUTO falls back to the hardware-scheduled
     // direct family (86.9 us at 8192^2), which beats the TMA family's static split (99.8 us).
@@ -522,7 +547,10 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         const char *d = getenv("B200DCT_TMA_STATIC");
         if (d && atoi(d) == 1) tma_dynamic = false;
     });
-    const bool tma_possible = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && !partials && get_encode() != nullptr &&
+    // fused metrics on the TMA family: f32 round trips of Haweel's T (the input tile is compared where it
+    // already is, in shared memory); everything else takes the direct family's metrics kernels
+    const bool metrics_tma_ok = !partials || (mode == MODE_RT && in.dt == DT_F32 && pl->tk == TK_HAWEEL && in.ptr != out.ptr);
+    const bool tma_possible = pl->path != B200DCT_PATH_DIRECT && prefer_tma && !shifted && metrics_tma_ok && get_encode() != nullptr &&
                               tma_plane_ok(in.ptr, in.dt, in.pitch, W) && tma_plane_ok(out.ptr, out.dt, out.pitch, W) &&
                               (!coef.ptr || tma_plane_ok(coef.ptr, coef.dt, coef.pitch, W));
     uint32_t *capture_sched = nullptr;
@@ -537,7 +565,8 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         for (int k = 6; k <= 10; k++)
             if (pl->mask == b200dct_zigzag_mask(k)) kmask = k;
 
-    const bool finv = !(kmask && !partials) && use_factored_inverse(pl, mode, pix); // compile-time-mask kernels keep the chains
+    if (partials) kmask = 0; // the metrics kernels take runtime masks
+    const bool finv = !kmask && use_factored_inverse(pl, mode, pix); // compile-time-mask kernels keep the chains
     if (use_tma) {
         TmaParams P;
         memset(&P, 0, sizeof(P));
@@ -545,6 +574,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
             return B200DCT_ERR_ARG;
         if (coef.ptr && !make_map(&P.coef_map, coef.ptr, coef.dt, coef.pitch, H, W)) return B200DCT_ERR_ARG;
         P.tiles_x = (uint32_t)((W + 255) / 256);
+        P.bx = (uint32_t)(W / 8);
         const unsigned long long nt = (unsigned long long)P.tiles_x * (unsigned long long)(H / 8);
         if (nt > 0x7fffffffull) return B200DCT_ERR_SHAPE;
         P.ntiles = (uint32_t)nt;
@@ -560,12 +590,13 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.buf_bytes = buf;
         // warps per CTA: the flavour's CTA size (8 for sparse-T f32; all the CTA holds for the
         // FP32-bound u8 and dense-T flavours), limited by 227 KiB of shared memory
-        const int max_w = tma_cta_threads(pix, pl->tk) / 32;
-        int nw = tma_warps > 0 ? tma_warps : (pix == DT_U8 || !pl->sparse ? max_w : B200DCT_TMA_DEFAULT_WARPS);
+        const int max_w = (partials ? B200DCT_TMA_CTA_THREADS_METRICS : tma_cta_threads(pix, pl->tk)) / 32;
+        int nw = tma_warps > 0 ? tma_warps : (pix == DT_U8 || !pl->sparse || partials ? max_w : B200DCT_TMA_DEFAULT_WARPS);
         if (nw > max_w) nw = max_w;
-        const int smem_w = (int)((227u * 1024u - 1024u) / (2u * buf + 8u));
+        const unsigned nbuf = partials ? 3u : 2u; // metrics: two input buffers per warp
+        const int smem_w = (int)((227u * 1024u - 1024u) / (nbuf * buf + 16u));
         if (nw > smem_w) nw = smem_w;
-        const size_t smem = (size_t)nw * 2 * buf + (size_t)nw * 8 + 1024;
+        const size_t smem = (size_t)nw * nbuf * buf + (size_t)nw * 16 + 1024;
         unsigned long long want = (nt + nw - 1) / nw;
         const unsigned long long gcap = (unsigned long long)(tma_grid > 0 ? tma_grid : di.sms);
         const int grid = (int)(want < gcap ? want : gcap);
@@ -573,11 +604,32 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         P.run = (uint32_t)tma_max_run;
         const unsigned long long tail = 2ull * (unsigned long long)grid * nw;
         P.run_tickets = nt > tail ? (uint32_t)((nt - tail) / P.run) : 0u;
+        // Metrics: with the dynamic scheduler the slot owns a zeroed integer triple and the last warp out
+        // folds it into acc -- one launch.  Static split: the first 24 bytes of the caller's workspace,
+        // zeroed before and folded after the kernel.
+        bool separate_finish = false;
+        if (partials) {
+            P.macc = sched_macc(P.sched);
+            P.acc = acc;
+            if (!P.macc) {
+                separate_finish = true;
+                P.acc = nullptr;
+                P.macc = reinterpret_cast<unsigned long long *>(partials);
+                const cudaError_t em = cudaMemsetAsync(P.macc, 0, 3 * sizeof(unsigned long long), stream);
+                if (em != cudaSuccess) return (int)em;
+            }
+        }
         cudaError_t e = kmask
                             ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing))
-                            : launch_tma(pl->tk, mode, qm, pix, finv, P, grid, nw * 32, smem, stream, pdl_for(capturing));
+                            : launch_tma(pl->tk, mode, qm, pix, finv, P, grid, nw * 32, smem, stream, pdl_for(capturing) && !separate_finish);
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
+        if (separate_finish) {
+            k_finish_fixed_point<<<1, 32, 0, stream>>>(P.macc, acc);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return (int)e;
+            tl_launches = 2;
+        }
         tl_path = "tma";
         return B200DCT_OK;
     }
@@ -599,6 +651,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     if (partials) {
         // fused metrics: per-CTA partials, then one fixed-order reduction into acc[0..2]
         if (mode != MODE_RT || in.ptr == out.ptr) return B200DCT_ERR_ARG;
+        kmask = 0;
         P.partials = partials;
         e = launch_direct_metrics(pl->tk, qm, pix, finv, P, grid, block, stream);
         if (e != cudaSuccess) return (int)e;

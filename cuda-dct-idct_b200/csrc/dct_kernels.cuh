@@ -365,169 +365,6 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     }
 }
 
-// ============================================================== any size, any alignment
-// Fused round trip of an image whose sides need not be multiples of 8 and whose rows need not be
-// aligned (SURVEY.md section 8f "generality"; the reference silently computes garbage there,
-// main_newAppr.cu:261-262): ONE pass, no scratch image.  Blocks that stick out over the right or
-// bottom edge are completed by edge replication (coordinates clamped to the last pixel, the same
-// values np.pad(mode="edge") produces) and only their inside part is stored.
-// Rows are only element-aligned, so accesses are scalar -- but coalesced: a warp owns 8 rows x 256
-// pixels (its 32 blocks), moves every row with 8 instructions of 32 consecutive elements, and
-// re-shapes rows <-> blocks through an 8 KiB shared-memory stage.  In-place calls are safe: a
-// warp reads all of its own region (and nothing else) before it writes it.
-struct AnyParams {
-    const void *in;
-    void *out;
-    size_t in_pitch, out_pitch; // bytes, any value >= W * element size
-    int H, W;
-    CommonParams cp;
-};
-
-template <int TK, int QMODE, int PIX, bool FINV = false>
-__global__ void __launch_bounds__(128, 5) k_any(const __grid_constant__ AnyParams P)
-{
-    constexpr bool BIASED = inverse_is_biased(TK, FINV);
-    using elem_t = typename std::conditional<PIX == DT_F32, float, uint8_t>::type;
-    __shared__ __align__(16) uint32_t stage[4][8 * 256];
-    const int lane = threadIdx.x;
-    const long long y0 = ((long long)blockIdx.x * 4 + threadIdx.y) * 8;
-    if (y0 >= P.H) return; // warp-uniform; lanes whose block lies outside the image stay for the row moves
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    uint32_t *st = stage[threadIdx.y];
-    const int xw = blockIdx.y * 256 + lane;
-
-    // rows -> stage (pixels - 128 as float), coordinates clamped to the image
-    int xs[8];
-    sfor<8>([&](auto s) { xs[IC(s)] = xw + 32 * IC(s) < P.W ? xw + 32 * IC(s) : P.W - 1; });
-    sfor<8>([&](auto r) {
-        const long long y = y0 + IC(r) < P.H ? y0 + IC(r) : P.H - 1;
-        const elem_t *row = reinterpret_cast<const elem_t *>((const char *)P.in + (size_t)y * P.in_pitch);
-        sfor<8>([&](auto s) { st[IC(r) * 256 + 32 * IC(s) + lane] = __float_as_uint((float)row[xs[IC(s)]] - 128.0f); });
-    });
-    __syncwarp();
-    float2 p[8][4];
-    sfor<8>([&](auto r) {
-        const float4 a = *reinterpret_cast<const float4 *>(st + IC(r) * 256 + lane * 8);
-        const float4 b = *reinterpret_cast<const float4 *>(st + IC(r) * 256 + lane * 8 + 4);
-        p[IC(r)][0] = make_float2(a.x, a.y); p[IC(r)][1] = make_float2(a.z, a.w);
-        p[IC(r)][2] = make_float2(b.x, b.y); p[IC(r)][3] = make_float2(b.z, b.w);
-    });
-    __syncwarp(); // every lane has its block: the stage can take the results
-
-    run_block<MODE_RT, TK, QMODE, true, FINV>(p, P.cp, [](float2 (&)[8][4]) {});
-
-    // blocks -> stage: the final element value (f32 bits, or the u8 value) per pixel
-    auto fin = [](float v) -> uint32_t {
-        const float o = BIASED ? v : v + 128.0f; // add_matrix_scalar, utils_kernels.cu:29
-        if constexpr (PIX == DT_F32) {
-            return __float_as_uint(o);
-        } else {
-            uint32_t b;
-            asm("cvt.rzi.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(o)); // convertToUnsignedChar, utils.cu:21
-            return b;
-        }
-    };
-    sfor<8>([&](auto r) {
-        *reinterpret_cast<uint4 *>(st + IC(r) * 256 + lane * 8) =
-            make_uint4(fin(p[IC(r)][0].x), fin(p[IC(r)][0].y), fin(p[IC(r)][1].x), fin(p[IC(r)][1].y));
-        *reinterpret_cast<uint4 *>(st + IC(r) * 256 + lane * 8 + 4) =
-            make_uint4(fin(p[IC(r)][2].x), fin(p[IC(r)][2].y), fin(p[IC(r)][3].x), fin(p[IC(r)][3].y));
-    });
-    __syncwarp();
-    sfor<8>([&](auto r) {
-        if (y0 + IC(r) < P.H) {
-            elem_t *row = reinterpret_cast<elem_t *>((char *)P.out + (size_t)(y0 + IC(r)) * P.out_pitch);
-            sfor<8>([&](auto s) {
-                if (xw + 32 * IC(s) < P.W) {
-                    const uint32_t v = st[IC(r) * 256 + 32 * IC(s) + lane];
-                    if constexpr (PIX == DT_F32) row[xw + 32 * IC(s)] = __uint_as_float(v);
-                    else row[xw + 32 * IC(s)] = (uint8_t)v;
-                }
-            });
-        }
-    });
-}
-
-// ---- 8-bit images of any size and alignment: no shared-memory stage at all.
-// Byte-aligned rows still consist of aligned 32-bit words: a lane fetches the three aligned words
-// that cover its block's 8-byte row and funnel-shifts its own 8 bytes out of them (3 LDG.32 + 2
-// SHF per row instead of 8 one-byte loads, conversions and a trip through shared memory), and on
-// the way out re-aligns with its left neighbour's last bytes (one SHFL + two SHF) so that almost
-// every store is an aligned 32-bit word; only the bytes at the two ends of a warp's 256-pixel span
-// and ragged blocks at the right image edge move as single bytes.  Bytes of neighbouring spans
-// that ride along in a loaded word are shifted out unused (so concurrent in-place updates of
-// them by other warps are harmless) and are never written.  Rows beyond the bottom edge and
-// pixels beyond the right edge replicate the last row / pixel (np.pad(mode="edge")).
-// 8191^2: 125 us with the staged kernel above -> see profiles/r02_any_size.txt.
-template <int TK, int QMODE, bool FINV>
-__global__ void __launch_bounds__(128, 5) k_any_u8(const __grid_constant__ AnyParams P)
-{
-    constexpr bool BIASED = inverse_is_biased(TK, FINV);
-    const int lane = threadIdx.x;
-    const long long y0 = ((long long)blockIdx.x * 4 + threadIdx.y) * 8;
-    if (y0 >= P.H) return; // warp-uniform
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int xb = blockIdx.y * 256 + lane * 8;       // first pixel of this lane's block
-    const bool full = xb + 8 <= P.W;                  // the whole block row lies inside the image
-    const bool partial = !full && xb < P.W;
-
-    float2 p[8][4];
-    sfor<8>([&](auto r) {
-        const long long y = y0 + IC(r) < P.H ? y0 + IC(r) : P.H - 1;
-        const uint8_t *row = (const uint8_t *)P.in + (size_t)y * P.in_pitch;
-        uint2 w = make_uint2(0u, 0u);
-        if (full) {
-            const uintptr_t a = (uintptr_t)(row + xb);
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-            const unsigned sh = (unsigned)(a & 3) * 8;   // warp-uniform: xb is a multiple of 8
-            const uint32_t w0 = wp[0], w1 = wp[1], w2 = sh ? wp[2] : 0u; // the third word holds own bytes iff sh != 0
-            w.x = __funnelshift_r(w0, w1, sh);
-            w.y = __funnelshift_r(w1, w2, sh);
-        } else if (partial) {
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t b = row[xb + k < P.W ? xb + k : P.W - 1];
-                if (k < 4) w.x |= b << (8 * k);
-                else w.y |= b << (8 * (k - 4));
-            }
-        }
-        unpack_u8_shifted(w, p[IC(r)]);
-    });
-
-    run_block<MODE_RT, TK, QMODE, true, FINV>(p, P.cp, [](float2 (&)[8][4]) {});
-
-    const bool next_full = __shfl_down_sync(0xffffffffu, (int)full, 1) && lane < 31;
-    sfor<8>([&](auto r) {
-        const uint2 o = BIASED ? pack_u8_row(p[IC(r)]) : pack_u8_plus128(p[IC(r)]);
-        const uint32_t left_hi = __shfl_up_sync(0xffffffffu, o.y, 1); // the left neighbour's last four bytes
-        if (y0 + IC(r) < P.H) {                                        // warp-uniform
-            uint8_t *dst = (uint8_t *)P.out + (size_t)(y0 + IC(r)) * P.out_pitch + xb;
-            if (full) {
-                const unsigned so = (unsigned)((uintptr_t)dst & 3);   // warp-uniform
-                uint32_t *q = reinterpret_cast<uint32_t *>((uintptr_t)dst & ~(uintptr_t)3);
-                if (so == 0) {
-                    q[0] = o.x;
-                    q[1] = o.y;
-                } else {
-                    const unsigned s = so * 8;
-                    if (lane > 0) q[0] = __funnelshift_l(left_hi, o.x, s); // neighbour's last `so` bytes + my first 4-so
-                    else
-                        for (unsigned k = 0; k < 4 - so; k++) dst[k] = (uint8_t)(o.x >> (8 * k));
-                    q[1] = __funnelshift_l(o.x, o.y, s);
-                    if (!next_full) // nobody to my right completes my last word
-                        for (unsigned k = 0; k < so; k++) dst[8 - so + k] = (uint8_t)(o.y >> (8 * (4 - so + k)));
-                }
-            } else if (partial) {
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (xb + k < P.W) dst[k] = (uint8_t)((k < 4 ? o.x : o.y) >> (8 * (k & 3)));
-            }
-        }
-    });
-}
-
 // ============================================================== TMA family
 // Tile = 8 image rows x 32 blocks (256 pixels).  Shared-memory images of a tile:
 //   f32 : 8 KiB, rows of 1 KiB = 8 segments of 128 B, hardware SWIZZLE_128B: the 16-byte
@@ -550,8 +387,14 @@ struct TmaParams {
     uint32_t run;         // tiles per ticket for the first run_tickets tickets, then 1
     uint32_t run_tickets;
     uint32_t buf_bytes;   // size of one tile buffer: the largest tile image among the planes of this call
+    // METRICS kernels: {sum (x-y)^2, sum x^2} in units of 2^-12 and the number of non-zero
+    // coefficients, accumulated with 64-bit integer atomics (order-independent => deterministic)
+    unsigned long long *macc;
+    double *acc;          // METRICS with the dynamic scheduler: the last warp out adds macc into acc[0..2] and re-zeroes macc
+    uint32_t bx;          // blocks per image row (lanes of a right-edge tile beyond it hold TMA zero fill, not pixels)
     CommonParams cp;
 };
+constexpr float METRICS_FIXED_POINT = 4096.0f;
 
 // every warp owns two tile buffers (in, out) of P.buf_bytes each: 8 KiB when an f32 plane is
 // involved, 4 KiB for i16, 2 KiB for an all-u8 round trip
@@ -695,20 +538,31 @@ __host__ __device__ constexpr int tma_cta_threads(int pix, int tk)
     return pix == DT_U8 ? B200DCT_TMA_CTA_THREADS_U8
                         : (tk == TK_HAWEEL ? B200DCT_TMA_CTA_THREADS : (tk == TK_DENSE_SYM ? B200DCT_TMA_CTA_THREADS_SYM : B200DCT_TMA_CTA_THREADS_DENSE));
 }
-#define B200DCT_TMA_BOUNDS __launch_bounds__(tma_cta_threads(PIX, TK), 1)
+// the metrics flavour carries three tile buffers per warp (24 KiB): nine warps fill the 227 KiB
+#ifndef B200DCT_TMA_CTA_THREADS_METRICS
+#define B200DCT_TMA_CTA_THREADS_METRICS 288
+#endif
+#define B200DCT_TMA_BOUNDS __launch_bounds__(METRICS ? B200DCT_TMA_CTA_THREADS_METRICS : tma_cta_threads(PIX, TK), 1)
 
-template <int MODE, int TK, int QMODE, int PIX, bool FINV = false>
+// METRICS (f32 round trips): the warp keeps TWO input buffers (the tile being transformed stays in
+// shared memory until its output exists, while the next tile is already arriving in the other one),
+// so the squared error and the signal energy are taken from the input tile where it already is
+// instead of re-reading it from global memory as the direct family's metrics kernel does.
+template <int MODE, int TK, int QMODE, int PIX, bool FINV = false, bool METRICS = false>
 __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
 {
+    static_assert(!METRICS || (MODE == MODE_RT && PIX == DT_F32), "fused metrics on the TMA family: f32 round trips");
     constexpr bool BIASED = inverse_is_biased(TK, FINV);
+    constexpr uint32_t NIN = METRICS ? 2u : 1u; // input buffers per warp
     extern __shared__ uint8_t smem_raw[];
     // 1 KiB alignment: the 128B swizzle pattern is a function of address bits 7..9
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
-    const uint32_t in_buf = smem_base + warp * 2 * P.buf_bytes;
-    const uint32_t out_buf = in_buf + P.buf_bytes;
-    const uint32_t bar = smem_base + nwarps * 2 * P.buf_bytes + warp * 8;
+    const uint32_t in_buf0 = smem_base + warp * (NIN + 1) * P.buf_bytes;
+    const uint32_t out_buf = in_buf0 + NIN * P.buf_bytes;
+    const uint32_t bar0 = smem_base + nwarps * (NIN + 1) * P.buf_bytes + warp * 8 * NIN;
+    uint32_t in_buf = in_buf0, bar = bar0; // METRICS: alternate between the two buffers / barriers
     const uint32_t off0 = f32_tile_off0(lane);
 
     // Dynamic tile scheduler.  The two dies / far and near L2 slices make SMs progress at
@@ -742,19 +596,21 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     const bool in_is_f32 = (MODE == MODE_INV) ? (P.coef_dt == DT_F32) : (PIX == DT_F32);
     const uint32_t in_bytes = (MODE == MODE_INV) ? (P.coef_dt == DT_F32 ? 8192u : 4096u) : tile_bytes<PIX>();
 
-    auto issue_load = [&](uint32_t t) {
+    auto issue_load_to = [&](uint32_t t, uint32_t buf, uint32_t b) {
         const int ty = (int)(t / P.tiles_x), tx = (int)(t - (uint32_t)ty * P.tiles_x);
-        mbar_expect_tx(bar, in_bytes);
-        if (in_is_f32) tma_load_3d(in_buf, &P.in_map, bar, 0, tx * 8, ty * 8);
-        else tma_load_2d(in_buf, &P.in_map, bar, tx * 256, ty * 8);
+        mbar_expect_tx(b, in_bytes);
+        if (in_is_f32) tma_load_3d(buf, &P.in_map, b, 0, tx * 8, ty * 8);
+        else tma_load_2d(buf, &P.in_map, b, tx * 256, ty * 8);
     };
+    auto issue_load = [&](uint32_t t) { issue_load_to(t, in_buf, bar); };
 
     // Programmatic dependent launch (only when the host asked for it; no-ops otherwise): let
     // the next kernel in the stream take this SM the moment this CTA leaves it, and do not
     // touch global memory before every earlier kernel has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (lane == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar0, 1);
+        if constexpr (METRICS) mbar_init(bar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #ifndef B200DCT_NO_TMAP_PREFETCH
         // the descriptors are kernel parameters, not data of the previous kernel: fetch them into
@@ -771,13 +627,27 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     if (lane == 0 && tile < P.ntiles) issue_load(tile);
     __syncwarp();
 
-    uint32_t parity = 0;
+    uint32_t parity = 0;   // METRICS: bit b = parity of barrier b
+    uint32_t cur = 0;      // METRICS: which input buffer holds the current tile
+    long long m_sse = 0, m_en = 0, m_nnz = 0;
     while (tile < P.ntiles) {
         const int ty = (int)(tile / P.tiles_x), tx = (int)(tile - (uint32_t)ty * P.tiles_x);
         uint32_t next_l0 = 0;
         if (lane == 0) next_l0 = claim_next(tile);
-        mbar_wait(bar, parity);
-        parity ^= 1;
+        uint32_t next_m = 0;
+        if constexpr (METRICS) {
+            // the other buffer was read for the last time at the end of the previous iteration: the
+            // next tile can start arriving before this one is even waited for
+            next_m = __shfl_sync(0xffffffffu, next_l0, 0);
+            if (lane == 0 && next_m < P.ntiles) issue_load_to(next_m, in_buf0 + (cur ^ 1u) * P.buf_bytes, bar0 + (cur ^ 1u) * 8);
+            in_buf = in_buf0 + cur * P.buf_bytes;
+            bar = bar0 + cur * 8;
+            mbar_wait(bar, (parity >> cur) & 1u);
+            parity ^= 1u << cur;
+        } else {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
 
         float2 p[8][4];
         // ---- shared -> registers
@@ -791,8 +661,13 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             sfor<8>([&](auto r) { unpack_u8_shifted(lds64u(in_buf + IC(r) * 256 + lane * 8), p[IC(r)]); });
         }
         // every lane has consumed its part of in_buf: re-arm it with the next tile
-        const uint32_t next = __shfl_sync(0xffffffffu, next_l0, 0); // also the warp-wide sync
-        if (lane == 0 && next < P.ntiles) issue_load(next);
+        uint32_t next;
+        if constexpr (METRICS) {
+            next = next_m;
+        } else {
+            next = __shfl_sync(0xffffffffu, next_l0, 0); // also the warp-wide sync
+            if (lane == 0 && next < P.ntiles) issue_load(next);
+        }
 
         auto put_coef_tile = [&](const CUtensorMap *map, float2 (&c)[8][4]) {
             if (lane == 0) tma_store_wait_read(); // previous store has drained out_buf
@@ -808,8 +683,16 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             }
         };
 
+        float t_nnz = 0.0f;
         run_block<MODE, TK, QMODE, true, FINV>(p, P.cp, [&](float2 (&c)[8][4]) {
             if (P.has_coef) put_coef_tile(&P.coef_map, c);
+            if constexpr (METRICS) {
+                sfor<8>([&](auto r) {
+                    sfor<4>([&](auto j) { // coefficients are integer-valued: min(|c|, 1) counts the non-zero ones
+                        t_nnz += fminf(fabsf(c[IC(r)][IC(j)].x), 1.0f) + fminf(fabsf(c[IC(r)][IC(j)].y), 1.0f);
+                    });
+                });
+            }
         });
 
         // ---- registers -> shared -> HBM
@@ -821,6 +704,25 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             if constexpr (PIX == DT_F32) {
                 if constexpr (!BIASED) sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); });
                 tile_st_f32(out_buf, off0, p);
+                if constexpr (METRICS) {
+                    // the pixels as stored against the pixels as read (still in this warp's input buffer)
+                    float t_sse = 0.0f, t_en = 0.0f;
+                    sfor<8>([&](auto r) {
+                        const float4 a = lds128(in_buf + IC(r) * 1024 + off0), b = lds128(in_buf + IC(r) * 1024 + (off0 ^ 16u));
+                        const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                        sfor<4>([&](auto j) {
+                            const float dx = x[2 * IC(j)] - p[IC(r)][IC(j)].x, dy = x[2 * IC(j) + 1] - p[IC(r)][IC(j)].y;
+                            t_sse = __fmaf_rn(dx, dx, t_sse); t_sse = __fmaf_rn(dy, dy, t_sse);
+                            t_en = __fmaf_rn(x[2 * IC(j)], x[2 * IC(j)], t_en); t_en = __fmaf_rn(x[2 * IC(j) + 1], x[2 * IC(j) + 1], t_en);
+                        });
+                    });
+                    // per-block sums (fixed order) -> 2^-12 fixed point: integer accumulation is order-independent
+                    if ((uint32_t)tx * 32u + (uint32_t)lane < P.bx) {
+                        m_sse += __float2ll_rn(t_sse * METRICS_FIXED_POINT);
+                        m_en += __float2ll_rn(t_en * METRICS_FIXED_POINT);
+                        m_nnz += (long long)t_nnz;
+                    }
+                }
             } else {
                 sfor<8>([&](auto r) { sts64u(out_buf + IC(r) * 256 + lane * 8, BIASED ? pack_u8_row(p[IC(r)]) : pack_u8_plus128(p[IC(r)])); });
             }
@@ -833,6 +735,19 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             }
         }
         tile = next;
+        if constexpr (METRICS) cur ^= 1u;
+    }
+    if constexpr (METRICS) {
+        for (int o = 16; o > 0; o >>= 1) {
+            m_sse += __shfl_xor_sync(0xffffffffu, m_sse, o);
+            m_en += __shfl_xor_sync(0xffffffffu, m_en, o);
+            m_nnz += __shfl_xor_sync(0xffffffffu, m_nnz, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&P.macc[0], (unsigned long long)m_sse);
+            atomicAdd(&P.macc[1], (unsigned long long)m_en);
+            atomicAdd(&P.macc[2], (unsigned long long)m_nnz);
+        }
     }
     if (lane == 0) {
         tma_store_wait_read();
@@ -840,6 +755,16 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             // every warp ends on exactly one losing ticket; the last warp out re-zeroes both counters
             __threadfence();
             if (atomicAdd(&sched[1], 1u) == stride - 1) {
+                if constexpr (METRICS) {
+                    if (P.acc) { // every other warp's sums are in (its atomics precede its fence + ticket)
+                        __threadfence();
+                        const long long sse = (long long)atomicExch(&P.macc[0], 0ull), en = (long long)atomicExch(&P.macc[1], 0ull),
+                                        nnz = (long long)atomicExch(&P.macc[2], 0ull);
+                        P.acc[0] += (double)sse / (double)METRICS_FIXED_POINT;
+                        P.acc[1] += (double)en / (double)METRICS_FIXED_POINT;
+                        P.acc[2] += (double)nnz;
+                    }
+                }
                 sched[0] = 0;
                 sched[1] = 0;
                 __threadfence();

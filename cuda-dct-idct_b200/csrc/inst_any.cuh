@@ -1,6 +1,6 @@
 // inst_any.cuh -- instantiates k_any (single-pass round trip for any image size and alignment)
 // for one pixel type: INST_PIX = DT_F32 / DT_U8, INST_TAG = name suffix.
-#include "dct_kernels.cuh"
+#include "any_kernels.cuh"
 
 namespace b200dct {
 

@@ -6,9 +6,10 @@ namespace b200dct {
 #define B200_CAT_(a, b) a##b
 #define B200_CAT(a, b) B200_CAT_(a, b)
 
-#define B200_TMA_CASE(M, X, F)                                                                        \
-    if (mode == (M) && pix == (X) && finv == (F)) {                                                   \
-        auto kern = k_tma<M, INST_SPARSE, INST_Q, X, F>;                                              \
+#define B200_TMA_CASE(M, X, F) B200_TMA_CASE_M(M, X, F, false)
+#define B200_TMA_CASE_M(M, X, F, MET)                                                                 \
+    if (mode == (M) && pix == (X) && finv == (F) && (P.macc != nullptr) == (MET)) {                   \
+        auto kern = k_tma<M, INST_SPARSE, INST_Q, X, F, MET>;                                         \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (e != cudaSuccess) return e;                                                               \
         cudaLaunchConfig_t cfg = {};                                                                  \
@@ -30,6 +31,7 @@ cudaError_t B200_CAT(launch_tma_, INST_TAG)(int mode, int pix, bool finv, const 
     B200_TMA_CASE(MODE_RT, DT_U8, false)
 #if INST_SPARSE == 1
     B200_TMA_CASE(MODE_RT, DT_U8, true)
+    B200_TMA_CASE_M(MODE_RT, DT_F32, false, true) // fused MSE / PEEN / non-zero count (P.macc != NULL)
 #endif
 #ifdef B200DCT_FAST_BUILD
 #if INST_Q == 0

@@ -1,6 +1,7 @@
 // plan_internal.h -- the plan object behind the opaque b200dct_plan handle (host TUs only).
 #pragma once
 #include "b200dct.h"
+#include "any_kernels.cuh"
 #include "rgb_kernels.cuh"
 
 struct b200dct_plan {

@@ -572,3 +572,33 @@ def test_any_size_u8_every_alignment(dct, oracle, W):
         assert np.array_equal(got[:, 3:3 + W], want)
         got[:, 3:3 + W] = 5
         assert (got == 5).all()
+
+
+@pytest.mark.parametrize("shape", [(8, 32), (256, 256), (72, 1056), (1024, 2048)])
+def test_fused_metrics_tma_family(dct, oracle, shape):
+    """The TMA family's metrics kernel (two input buffers per warp, error taken from the input tile
+    in shared memory, 64-bit fixed-point accumulation): pixels and coefficients bit-exact, MSE/PEEN
+    to 1e-6 of the oracle's doubles, non-zero count exact, and -- integer accumulation -- the SAME
+    value bit for bit from run to run although tiles are scheduled dynamically."""
+    img = inputs.float_noise(*shape, seed=5)
+    for keep in (dct.ALL_COEFFS, oracle.zigzag_mask(10)):
+        want, wcoef = oracle.roundtrip(img, keep=keep, want_coef=True)
+        wm, wp = oracle.metrics(img, want)
+        plan = dct.Plan(keep=keep, path=PATHS["tma"])
+        seen = set()
+        for rep in range(4):
+            coef = torch.empty(shape, dtype=torch.float32, device="cuda")
+            out, (mse, peen, nnz) = dct.roundtrip_with_metrics(dev(img), coef=coef if rep % 2 else None, plan=plan)
+            assert dct.api.last_path() == "tma" and dct.api.last_launch_count() == 1
+            assert np.array_equal(bits(host(out)), bits(want))
+            if rep % 2:
+                assert np.array_equal(bits(host(coef)), bits(wcoef))
+            assert mse == pytest.approx(wm, rel=1e-6) and peen == pytest.approx(wp, rel=1e-6)
+            assert nnz == int(np.count_nonzero(wcoef))
+            seen.add((mse, peen))
+        assert len(seen) == 1, "fixed-point accumulation must not depend on the tile schedule"
+    # accumulating calls ADD into the caller's accumulators on both families
+    x = dev(img)
+    for path in ("tma", "direct"):
+        _, (m1, _, n1) = dct.roundtrip_with_metrics(x, plan=dct.Plan(path=PATHS[path]))
+        assert m1 == pytest.approx(oracle.metrics(img, oracle.roundtrip(img))[0], rel=1e-6)

@@ -2,7 +2,7 @@
 """Turns the ncu artefacts a gpurun call left in gpurun_out/ into the committed summaries
 under profiles/ (run here, no GPU needed):
 
-    python tools/ncu_summary.py r01 gpurun_out/prof_tma_f32_dyn8.ncu-rep gpurun_out/launches.csv
+    python tools/ncu_summary.py r01 gpurun_out/prof_tma_f32_dyn8.ncu-rep gpurun_out/launches.csv [--no-traffic] [--tag 16384]
 
 writes profiles/<round>_ncu_<kernel>.txt (key metrics of every captured launch),
 profiles/<round>_launches.txt (per-kernel share of the launch list) and
@@ -46,7 +46,13 @@ def raw(rep):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if a != "--no-traffic"]
+    tag = ""
+    argv = list(sys.argv[1:])
+    if "--tag" in argv:          # suffix of the summary's file name (same kernel at two sizes)
+        i = argv.index("--tag")
+        tag = "_" + argv[i + 1]
+        del argv[i:i + 2]
+    args = [a for a in argv if a != "--no-traffic"]
     write_traffic = "--no-traffic" not in sys.argv     # only the headline kernel feeds bench.py's roofline.traffic
     rnd, rep = args[0], args[1]
     launches = args[2] if len(args) > 2 else None
@@ -60,6 +66,7 @@ def main():
         if k in hdr:
             i = hdr.index(k)
             lines.append(f"{k:75s} {units[i]:14s} " + "  ".join(r[i] for r in data))
+    short += tag
     with open(f"profiles/{rnd}_ncu_{short}.txt", "w") as f:
         f.write("\n".join(lines) + "\n")
     rd = [float(r[hdr.index("dram__bytes_read.sum")]) for r in data]
