@@ -27,18 +27,18 @@ def circuit_like(n: int, seed: int = 7) -> np.ndarray:
     rng = np.random.default_rng(seed)
     yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
     img = 40 + 25 * (xx / n) + 15 * np.sin(yy / n * 3.1)            # illumination
-    for _ in range(n // 16):                                          # traces
+    for _ in range(n // 2):                                           # traces
         x0, y0 = rng.integers(0, n, 2)
-        length, width = int(rng.integers(n // 16, n // 2)), int(rng.integers(2, 7))
+        length, width = int(rng.integers(n // 32, n // 4)), int(rng.integers(2, 9))
         level = float(rng.integers(120, 230))
         if rng.random() < 0.5:
             img[y0:y0 + width, x0:x0 + length] = level
         else:
             img[y0:y0 + length, x0:x0 + width] = level
-    for _ in range(n // 32):                                          # pads
+    for _ in range(n // 4):                                           # pads
         x0, y0, r = int(rng.integers(0, n)), int(rng.integers(0, n)), int(rng.integers(4, 12))
         img[(xx - x0) ** 2 + (yy - y0) ** 2 < r * r] = 245
-    img += rng.normal(0, 2.0, img.shape)
+    img += rng.normal(0, 4.0, img.shape)
     return img.clip(0, 255).astype(np.uint8)
 
 

@@ -103,6 +103,8 @@ def compat_lib() -> C.CDLL:
         L.b200dct_compat_set_keep_mask.argtypes = [C.c_uint64]
         L.b200dct_compat_set_options.argtypes = [i, i]
         L.b200dct_compat_set_options.restype = None
+        L.b200dct_compat_cache_transform.argtypes = [i]
+        L.b200dct_compat_cache_transform.restype = None
         L.b200dct_compat_last_ms.restype = C.c_float
         for f in (L.b200dct_compat_dct, L.b200dct_compat_idct, L.b200dct_compat_idct_inplace_dequant):
             f.argtypes = [vp, i, i, vp, vp]

@@ -884,6 +884,18 @@ extern "C" int b200dct_selftest_division(float d, unsigned long long first, unsi
     return e == cudaSuccess ? B200DCT_OK : (int)e;
 }
 
+// Launches made under stream capture take a ticket-counter pair for good (CUDA offers no hook to
+// return it when the graph is destroyed): a long-lived process that keeps re-capturing can ask how
+// many are left; once they are gone captured AUTO launches take the direct family (b200dct_last_path
+// says "direct"), they never fail.
+extern "C" int b200dct_capture_slots_left(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return B200DCT_ERR_NODEVICE;
+    std::lock_guard<std::mutex> lk(g_sched.mu);
+    return CAPTURE_SLOTS - (int)g_sched.next_capture[dev];
+}
+
 extern "C" int b200dct_last_launch_count(void) { return tl_launches; }
 extern "C" const char *b200dct_last_path(void) { return tl_path; }
 

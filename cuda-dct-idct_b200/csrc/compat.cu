@@ -23,6 +23,12 @@ struct CompatState {
     b200dct_plan *plan = nullptr;
     float last_T[64];
     bool have_T = false;
+    bool cache_T = false;          // opt-in: trust the device pointer, skip the per-call fetch
+    const float *cached_ptr = nullptr;
+    float *d_q = nullptr;          // device copy of Q for cublasDCTv2's in-place dequantisation
+    float d_q_host[64];
+    bool d_q_valid = false;
+    int sms = 0;
     bool side_effects = true;
     bool print_timing = true;
     float last_ms = 0.0f;
@@ -40,6 +46,11 @@ b200dct_plan *plan()
 // its 256 bytes and re-plan only when the contents change.
 void sync_transform(const float *d_T)
 {
+    // b200dct_compat_cache_transform(1): the caller promises that the 64 floats behind a given device
+    // pointer do not change between calls (true for every reference program: T is uploaded once,
+    // main_newAppr.cu:88-95), so the blocking 256-byte D2H copy in front of every call is skipped
+    if (g.cache_T && g.have_T && d_T == g.cached_ptr) return;
+    g.cached_ptr = d_T;
     float t[64];
     COMPAT_CHECK(cudaMemcpy(t, d_T, sizeof(t), cudaMemcpyDeviceToHost));
     if (!g.have_T || memcmp(t, g.last_T, sizeof(t)) != 0) {
@@ -86,12 +97,37 @@ __global__ void k_dequant_inplace(float *c, const float *q, int W, size_t n)
     }
 }
 
-void inverse(const float *coef, int H, int W, const float *d_T, float *result)
+// dequant_in_place: cublasDCTv2 leaves its coefficient buffer dequantised (main_cublass_2.cu:282).  The
+// transform reads the ORIGINAL coefficients in one fused pass; the in-place product is then written by
+// a small element-wise kernel in the same stream, inside the timed and synchronised region, so the
+// caller observes the same buffer contents as with the reference when the call returns.
+void inverse(const float *coef, int H, int W, const float *d_T, float *result, float *dequant_in_place = nullptr)
 {
     sync_transform(d_T);
     const size_t pitch = (size_t)W * sizeof(float);
+    if (dequant_in_place) {
+        float q[64];
+        COMPAT_CHECK(b200dct_plan_get_quant(plan(), q));
+        if (!g.d_q) COMPAT_CHECK(cudaMalloc(&g.d_q, sizeof(q)));
+        if (!g.d_q_valid || memcmp(q, g.d_q_host, sizeof(q)) != 0) { // upload only when the table changed
+            COMPAT_CHECK(cudaMemcpy(g.d_q, q, sizeof(q), cudaMemcpyHostToDevice));
+            memcpy(g.d_q_host, q, sizeof(q));
+            g.d_q_valid = true;
+        }
+        if (!g.sms) {
+            int dev = 0;
+            COMPAT_CHECK(cudaGetDevice(&dev));
+            COMPAT_CHECK(cudaDeviceGetAttribute(&g.sms, cudaDevAttrMultiProcessorCount, dev));
+        }
+    }
     timer_start();
     COMPAT_CHECK(b200dct_inverse(plan(), coef, B200DCT_F32, pitch, result, B200DCT_F32, pitch, H, W, nullptr));
+    if (dequant_in_place) {
+        const size_t n = (size_t)H * W;
+        size_t blocks = (n + 255) / 256;
+        if (blocks > (size_t)g.sms * 8) blocks = (size_t)g.sms * 8;
+        k_dequant_inplace<<<(unsigned)blocks, 256>>>(dequant_in_place, g.d_q, W, n);
+    }
     timer_stop("IDCT", W, H);
 }
 
@@ -121,24 +157,11 @@ void idct_all_blocks(const float *image_matrix, int img_height, int img_width, c
     inverse(image_matrix, img_height, img_width, transform_matrix, result);
 }
 
-// cublasDCTv2: the coefficient buffer is dequantised in place before the transform
-// (main_cublass_2.cu:282).  The transform itself reads the ORIGINAL coefficients in one
-// fused pass; the in-place product is then written by a small element-wise kernel, so
-// the caller observes the same buffer contents as with the reference.
+// cublasDCTv2 (non-const input): see inverse()
 void idct_all_blocks(float *image_matrix, int img_height, int img_width, const float *transform_matrix,
                      float *result, cublasHandle_t)
 {
-    inverse(image_matrix, img_height, img_width, transform_matrix, result);
-    if (g.side_effects) {
-        static thread_local float *d_q = nullptr;
-        if (!d_q) COMPAT_CHECK(cudaMalloc(&d_q, 64 * sizeof(float)));
-        float q[64];
-        COMPAT_CHECK(b200dct_plan_get_quant(plan(), q));
-        COMPAT_CHECK(cudaMemcpy(d_q, q, sizeof(q), cudaMemcpyHostToDevice));
-        const size_t n = (size_t)img_height * img_width;
-        k_dequant_inplace<<<1184, 256>>>(image_matrix, d_q, img_width, n);
-        COMPAT_CHECK(cudaDeviceSynchronize());
-    }
+    inverse(image_matrix, img_height, img_width, transform_matrix, result, g.side_effects ? image_matrix : nullptr);
 }
 
 extern "C" {
@@ -152,6 +175,11 @@ void b200dct_compat_set_options(int side_effects, int print_timing)
 {
     g.side_effects = side_effects != 0;
     g.print_timing = print_timing != 0;
+}
+void b200dct_compat_cache_transform(int on)
+{
+    g.cache_T = on != 0;
+    g.cached_ptr = nullptr; // also the way to invalidate: the next call fetches T again
 }
 float b200dct_compat_last_ms(void) { return g.last_ms; }
 void b200dct_compat_dct(float *image, int H, int W, const float *d_T, float *result) { dct_all_blocks_cuda(image, H, W, d_T, result); }

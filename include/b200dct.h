@@ -299,6 +299,11 @@ int b200dct_selftest_division(float d, unsigned long long first, unsigned long l
 
 /* How many kernels the last call on this thread launched (for bench accounting). */
 int b200dct_last_launch_count(void);
+/* Kernels launched under stream capture by the persistent (TMA) family own a scheduler slot for the
+ * life of the process (4096 per device; a graph replays its slot, CUDA has no destroy hook to hand
+ * it back).  Returns how many are left on the current device; at 0 captured AUTO launches run the
+ * direct kernel family instead (about 5 % slower at 8192^2), b200dct_last_path() reports which. */
+int b200dct_capture_slots_left(void);
 /* Name of the kernel family the last call on this thread used: "tma", "direct" or "any". */
 const char *b200dct_last_path(void);
 

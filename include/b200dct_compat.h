@@ -60,6 +60,13 @@ int b200dct_compat_set_keep_mask(uint64_t mask);
 /* side_effects: 1 (default) reproduces the in-place input mutations listed above, 0 skips
  * them (saves 4 B/px of traffic).  print_timing: 1 (default) prints the reference's lines. */
 void b200dct_compat_set_options(int side_effects, int print_timing);
+/* The reference passes T as a device pointer on every call (main_newAppr.cu:99), so by default every
+ * call fetches its 64 floats (a blocking 256-byte device-to-host copy) and re-plans if they changed.
+ * on = 1: the caller promises that the contents behind a given pointer stay the same (every reference
+ * program uploads T once, main_newAppr.cu:88-95); T is then fetched only when the POINTER changes.
+ * Calling it again (with 0 or 1) drops the cached pointer.  Worth 10-20 us per call: at 256^2 the
+ * kernels themselves take 3.5 us (profiles/r02_compat_small.txt). */
+void b200dct_compat_cache_transform(int on);
 /* Device milliseconds of the kernels of the last dct_ / idct_ call on this thread. */
 float b200dct_compat_last_ms(void);
 

@@ -107,10 +107,13 @@ def test_cuda_graph_capture(dct, oracle, path, expect):
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     s = torch.cuda.Stream()
+    slots_before = int(dct.lib().b200dct_capture_slots_left())
     with torch.cuda.graph(g, stream=s):
         dct.roundtrip(img, out=out, plan=plan, stream=torch.cuda.current_stream())
         captured_path = dct.api.last_path()
     assert captured_path == expect
+    # a captured TMA launch keeps one scheduler slot for good; the count is visible to the caller
+    assert int(dct.lib().b200dct_capture_slots_left()) == slots_before - (1 if expect == "tma" else 0)
     out.zero_()
     other = torch.empty_like(img)
     for _ in range(3):
