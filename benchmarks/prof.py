@@ -2,7 +2,7 @@
 """Driver for ncu captures: runs a few launches of ONE kernel flavour and exits.
 
     python benchmarks/prof.py <case> [N] [launches]
-    cases: f32 (headline, TMA family) | f32_direct | u8 | u8_exact | u8_k10 | dense_sym | dense_chain |
+    cases: f32 (headline, TMA family) | f32_direct | u8 | u8_exact | u8_k10 | dense_sym | dense_chain | dense_mma |
            rgb | any_f32 | any_u8 | metrics_f32 | metrics_u8 | fwd | inv | zigzag_fwd | coded_bits
 
 Used as
@@ -31,7 +31,7 @@ def main():
     dev = "cuda"
     x32 = torch.randint(0, 256, (N, N), device=dev, dtype=torch.int32).float()
     f = {}
-    if case in ("f32", "f32_direct", "dense_sym", "dense_chain", "metrics_f32", "fwd", "inv", "zigzag_fwd"):
+    if case in ("f32", "f32_direct", "dense_sym", "dense_chain", "dense_mma", "metrics_f32", "fwd", "inv", "zigzag_fwd"):
         a = [x32.clone() for _ in range(2)]
         b = [torch.empty_like(x32) for _ in range(2)]
     if case == "f32":
@@ -40,8 +40,9 @@ def main():
     elif case == "f32_direct":
         plan = m.Plan(path=m.api.PATH_DIRECT)
         step = lambda i: m.roundtrip(a[i % 2], out=b[i % 2], plan=plan)
-    elif case in ("dense_sym", "dense_chain"):
-        plan = m.Plan(T=dct2(), dense=m.api.DENSE_CHAIN if case == "dense_chain" else m.api.DENSE_AUTO)
+    elif case in ("dense_sym", "dense_chain", "dense_mma"):
+        plan = m.Plan(T=dct2(), dense={"dense_chain": m.api.DENSE_CHAIN, "dense_mma": m.api.DENSE_MMA}.get(case, m.api.DENSE_AUTO),
+                      path=m.api.PATH_DIRECT)
         step = lambda i: m.roundtrip(a[i % 2], out=b[i % 2], plan=plan)
     elif case == "fwd":
         plan = m.Plan()

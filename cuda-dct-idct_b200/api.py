@@ -19,7 +19,7 @@ ALL_COEFFS = (1 << 64) - 1
 F32, U8, I16, I16_ZIGZAG = 0, 1, 2, 3
 PATH_AUTO, PATH_DIRECT, PATH_TMA = 0, 1, 2
 INVERSE_AUTO, INVERSE_EXACT, INVERSE_FACTORED = 0, 1, 2
-DENSE_AUTO, DENSE_CHAIN, DENSE_SYMMETRIC = 0, 1, 2
+DENSE_AUTO, DENSE_CHAIN, DENSE_SYMMETRIC, DENSE_MMA = 0, 1, 2, 3
 
 
 class B200DCTError(RuntimeError):
@@ -182,7 +182,8 @@ class Plan:
 
     def set_dense(self, mode: int) -> None:
         """DENSE_CHAIN: ordered FMA chains for a dense T (bit-identical to the reference's chain order with that T);
-        DENSE_AUTO / DENSE_SYMMETRIC: even/odd evaluation when T has the DCT-II symmetry."""
+        DENSE_AUTO / DENSE_SYMMETRIC: even/odd evaluation when T has the DCT-II symmetry;
+        DENSE_MMA: the tensor-core arm (f32 fused round trips on mma.sync TF32 with hi/lo splits), opt-in."""
         _check(lib().b200dct_plan_set_dense(self._h, mode))
 
     @property

@@ -15,6 +15,7 @@
 
 #include "any_kernels.cuh"
 #include "rgb_kernels.cuh"
+#include "mma_kernels.cuh"
 
 namespace b200dct {
 // one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
@@ -27,6 +28,7 @@ B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2) B200_DECL(
 cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_direct_k.cu
 cudaError_t launch_any_f32(int tk, int qm, bool finv, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_any_f32.cu
 cudaError_t launch_any_u8(int tk, int qm, bool finv, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);  // inst_any_u8.cu
+cudaError_t launch_mma(bool fastdiv, const MmaParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);                           // inst_mma.cu
 cudaError_t launch_tma_kmask(int k, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
 
 static cudaError_t launch_direct(int tk, int mode, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
@@ -175,6 +177,7 @@ extern "C" int b200dct_plan_create(b200dct_plan **out)
     if (const char *e = getenv("B200DCT_DENSE")) {
         if (!strcmp(e, "chain")) pl->dense = B200DCT_DENSE_CHAIN;
         else if (!strcmp(e, "symmetric")) pl->dense = B200DCT_DENSE_SYMMETRIC;
+        else if (!strcmp(e, "mma")) pl->dense = B200DCT_DENSE_MMA;
     }
     // env B200DCT_INVERSE=exact|factored|auto: default inverse mode of new plans (a caller that wants
     // the reference's u8 bits everywhere, e.g. through the compat library, sets "exact")
@@ -278,7 +281,7 @@ extern "C" int b200dct_plan_set_inverse(b200dct_plan *pl, b200dct_inverse_mode m
 
 extern "C" int b200dct_plan_set_dense(b200dct_plan *pl, b200dct_dense_mode mode)
 {
-    if (!pl || mode < B200DCT_DENSE_AUTO || mode > B200DCT_DENSE_SYMMETRIC) return B200DCT_ERR_ARG;
+    if (!pl || mode < B200DCT_DENSE_AUTO || mode > B200DCT_DENSE_MMA) return B200DCT_ERR_ARG;
     pl->dense = mode;
     plan_refresh(pl);
     return B200DCT_OK;
@@ -567,6 +570,25 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
 
     if (partials) kmask = 0; // the metrics kernels take runtime masks
     const bool finv = !kmask && use_factored_inverse(pl, mode, pix); // compile-time-mask kernels keep the chains
+    // the tensor-core arm of the dense variant (opt-in): f32 fused round trips, optional f32 coefficient plane
+    if (pl->dense == B200DCT_DENSE_MMA && !pl->sparse && mode == MODE_RT && in.dt == DT_F32 && !partials && !shifted &&
+        (!coef.ptr || coef.dt == DT_F32)) {
+        MmaParams M;
+        memset(&M, 0, sizeof(M));
+        M.in = (const float *)in.ptr; M.in_pitch = in.pitch;
+        M.out = (float *)const_cast<void *>(out.ptr); M.out_pitch = out.pitch;
+        M.coef = (float *)const_cast<void *>(coef.ptr); M.coef_pitch = coef.pitch;
+        M.bx = W / 8; M.by = H / 8;
+        M.cp = pl->cp;
+        dim3 mblock(32, 4), mgrid((unsigned)((M.by + 3) / 4), (unsigned)((M.bx + 31) / 32));
+        if (mgrid.y > 65535u) return B200DCT_ERR_SHAPE;
+        const cudaError_t em = launch_mma(pl->q_fastdiv, M, mgrid, mblock, stream, pdl_for(capturing));
+        if (em != cudaSuccess) return (int)em;
+        tl_launches = 1;
+        tl_path = "mma";
+        return B200DCT_OK;
+    }
+
     if (use_tma) {
         TmaParams P;
         memset(&P, 0, sizeof(P));

@@ -102,7 +102,7 @@ typedef enum b200dct_inverse_mode {
 /* How a DENSE T (anything that is not bit-identical to Haweel's matrix: the "exact DCT" of the
  * cublasDCT / cublasDCTv2 variants, main_cublass.cu:85-93) is evaluated.
  *   CHAIN     : every inner product as the ascending chain of 8 FMAs (the order of the reference's
- *               non-cuBLAS kernels; bit-identical to oracle/dct_oracle.c with that T).
+ *               non-cuBLAS kernels; bit-identical to the CPU restatement of that order with that T).
  *   SYMMETRIC : if T's even rows are symmetric and its odd rows antisymmetric (T[k][n] == +-T[k][7-n],
  *               true of the DCT-II), evaluate it through its even/odd halves: 40 instead of 64
  *               operations per 8-point transform in both directions.  Sums are re-associated; the
@@ -110,11 +110,17 @@ typedef enum b200dct_inverse_mode {
  *               already differs from any fixed chain in 1e-4..1e-3 of the quantised coefficients, so
  *               the criterion is the mismatch COUNT against live cuBLAS (tests/test_gpu_reference.py),
  *               pixels within 1 LSB.  A T without the structure runs CHAIN.
- *   AUTO      : SYMMETRIC where T has the structure.  Default. */
+ *   AUTO      : SYMMETRIC where T has the structure.  Default.
+ *   MMA       : the tensor-core arm (BASELINE configs[3] "CUDA-core vs tensor-core path"): f32 fused
+ *               round trips run as batched 8x8 contractions on mma.sync m16n8k8 TF32 with the 2-term
+ *               hi/lo split of both operands (FP32-grade inner products, FP32 accumulation); every
+ *               other call of the plan runs SYMMETRIC / CHAIN.  Opt-in only: measured against the
+ *               CUDA-core kernels with ncu it does not win, so AUTO never picks it. */
 typedef enum b200dct_dense_mode {
     B200DCT_DENSE_AUTO = 0,
     B200DCT_DENSE_CHAIN = 1,
-    B200DCT_DENSE_SYMMETRIC = 2
+    B200DCT_DENSE_SYMMETRIC = 2,
+    B200DCT_DENSE_MMA = 3
 } b200dct_dense_mode;
 
 typedef struct b200dct_plan b200dct_plan;

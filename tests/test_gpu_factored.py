@@ -250,3 +250,45 @@ def test_symmetric_dense_full_size_16384(dct, oracle):
     oc = dct.roundtrip(img, plan=dct.Plan(T=T, dense=dct.api.DENSE_CHAIN))
     for r0 in (0, N - 16):
         assert np.array_equal(bits(host(oc[r0:r0 + 16])), bits(oracle.roundtrip(host(img[r0:r0 + 16]), T=T)))
+
+
+@pytest.mark.factored
+@pytest.mark.parametrize("shape", [(8, 8), (256, 256), (72, 1048), (1024, 1024)])
+def test_tensor_core_arm_of_the_dense_variant(dct, oracle, shape):
+    """DENSE_MMA (BASELINE configs[3], tensor-core path): batched 8x8 contractions on mma.sync TF32
+    with hi/lo operand splits.  Same criterion as every dense-T arithmetic that re-associates sums
+    (cuBLAS included): quantised coefficients differ from the ordered FP32 chain in at most a few
+    1e-4 of the positions and then by one step; pixels within 1 LSB after the 8-bit conversion;
+    MSE / PEEN within 1e-3."""
+    T = oracle.dct2_T()
+    img = oracle.rand_image(*shape, 11)
+    want, wcoef = oracle.roundtrip(img, T=T, want_coef=True)
+    plan = dct.Plan(T=T, dense=dct.api.DENSE_MMA)
+    d = torch.from_numpy(img).cuda()
+    coef = torch.empty_like(d)
+    out = dct.roundtrip(d, coef=coef, plan=plan)
+    assert dct.api.last_path() == "mma"
+    torch.cuda.synchronize()
+    gc, go = coef.cpu().numpy(), out.cpu().numpy()
+    diff = np.abs(gc - wcoef)
+    frac = float(np.mean(diff > 0))
+    assert diff.max() <= 1 and frac < 2e-3, (diff.max(), frac)
+    same = diff.reshape(shape[0] // 8, 8, shape[1] // 8, 8).max(axis=(1, 3)) == 0       # blocks with identical coefficients
+    pix = np.abs(go - want).reshape(shape[0] // 8, 8, shape[1] // 8, 8).max(axis=(1, 3))
+    assert pix[same].max() < 2e-3                                                        # same coefficients -> same pixels up to FP32 rounding
+    assert np.abs(oracle.to_u8(go).astype(np.int16) - oracle.to_u8(want).astype(np.int16)).max() <= 1 or frac > 0
+    m_w, p_w = oracle.metrics(img, want)
+    m_g, p_g = oracle.metrics(img, go)
+    assert abs(m_g - m_w) <= 1e-3 * m_w and abs(p_g - p_w) <= 1e-3 * p_w
+    # without the coefficient plane, masks and custom tables, non-integer divisors (IEEE division kernel)
+    out2 = dct.roundtrip(d, plan=plan)
+    assert torch.equal(out2, out)
+    for Q, keep in ((oracle.jpeg_Q() * 2, oracle.zigzag_mask(10)), (oracle.jpeg_Q() * 0.37, dct.ALL_COEFFS)):
+        w2, c2 = oracle.roundtrip(img, T=T, Q=Q, keep=keep, want_coef=True)
+        cf = torch.empty_like(d)
+        dct.roundtrip(d, coef=cf, plan=dct.Plan(T=T, Q=Q, keep=keep, dense=dct.api.DENSE_MMA))
+        dd = np.abs(cf.cpu().numpy() - c2)
+        assert dd.max() <= 1 and np.mean(dd > 0) < 2e-3
+    # every other call of such a plan runs the CUDA-core kernels
+    c16 = dct.forward(d, plan=plan)
+    assert dct.api.last_path() in ("direct", "tma")
