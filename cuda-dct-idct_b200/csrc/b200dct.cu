@@ -449,6 +449,80 @@ unsigned long long *sched_macc(const uint32_t *slot)
 }
 } // namespace
 
+// ---- early tile loads across launch boundaries
+// With programmatic dependent launch a kernel's CTAs start while its predecessor drains, but may not
+// touch memory before griddepcontrol.wait: at every launch boundary HBM sees a write-only tail followed
+// by a read-only ramp ("where the last 5 % go").  If nothing the new launch READS is
+// written by the launch it can overlap with, its loads need not wait -- only its writes do.  The
+// library establishes that by itself, per (device, stream):
+//   * the relaxation only ever applies to the immediately preceding kernel of the stream, and only if
+//     that kernel triggers launch_dependents -- i.e. one of this library's; anything else the caller
+//     enqueues in between (copies, other kernels) restores full stream order by itself;
+//   * when that predecessor is a persistent TMA-family launch that fills the machine (one CTA on every SM, more than half of an SM's
+//     registers or shared memory, so a successor CTA starts only where a predecessor CTA has EXITED,
+//     which it cannot do before having passed its own wait), everything older than the predecessor
+//     is complete by the time a successor CTA runs: only the predecessor's writes matter;
+//   * so: predecessor on this stream = TMA family, and [input plane] disjoint from its output /
+//     coefficient planes  =>  early_loads.  Every other launch of the library clears the record.
+// Not under stream capture.  env B200DCT_EARLY_LOADS=0 disables (A/B).
+namespace {
+struct Range {
+    uintptr_t lo = 0, hi = 0; // [lo, hi)
+};
+struct LastLaunch {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    bool tma = false;
+    Range w[2];
+};
+constexpr int LAST_SLOTS = 16;
+LastLaunch g_last[LAST_SLOTS];
+std::mutex g_last_mu;
+Range plane_range(const void *p, size_t pitch, size_t row_bytes, int H)
+{
+    Range r;
+    if (p) {
+        r.lo = (uintptr_t)p;
+        r.hi = r.lo + (size_t)(H - 1) * pitch + row_bytes;
+    }
+    return r;
+}
+bool disjoint(const Range &a, const Range &b) { return a.hi <= b.lo || b.hi <= a.lo || a.lo == a.hi || b.lo == b.hi; }
+bool early_loads_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *p = getenv("B200DCT_EARLY_LOADS");
+        v = (p && atoi(p) == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+// Returns whether a TMA launch reading `rd` on `stream` may load early, and records this launch.
+bool record_launch(cudaStream_t stream, bool tma, const Range &rd, const Range &w0, const Range &w1)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lk(g_last_mu);
+    LastLaunch *e = nullptr, *freeslot = nullptr;
+    for (auto &x : g_last) {
+        if (x.dev == dev && x.stream == stream) e = &x;
+        if (x.dev < 0 && !freeslot) freeslot = &x;
+    }
+    bool early = false;
+    if (e) early = tma && e->tma && disjoint(rd, e->w[0]) && disjoint(rd, e->w[1]);
+    if (!e) e = freeslot ? freeslot : &g_last[((uintptr_t)stream >> 4) % LAST_SLOTS]; // evicting a record is always safe (no early loads)
+    e->dev = dev;
+    e->stream = stream;
+    e->tma = tma;
+    e->w[0] = w0;
+    e->w[1] = w1;
+    return early && early_loads_enabled();
+}
+} // namespace
+namespace b200dct {
+void forget_stream(cudaStream_t s) { record_launch(s, false, Range{}, Range{}, Range{}); }
+}
+
 static bool tma_dynamic = true; // env B200DCT_TMA_STATIC=1 forces the static tile split
 static int tma_warps = 0; // env B200DCT_TMA_WARPS: warps per CTA of the persistent kernel (0 = per-flavour default; clamped to the kernel's CTA size and to shared memory)
 static int tma_max_run = 2;                       // env B200DCT_TMA_RUN: longest run of tiles per claim
@@ -582,6 +656,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         M.cp = pl->cp;
         dim3 mblock(32, 4), mgrid((unsigned)((M.by + 3) / 4), (unsigned)((M.bx + 31) / 32));
         if (mgrid.y > 65535u) return B200DCT_ERR_SHAPE;
+        forget_stream(stream);
         const cudaError_t em = launch_mma(pl->q_fastdiv, M, mgrid, mblock, stream, pdl_for(capturing));
         if (em != cudaSuccess) return (int)em;
         tl_launches = 1;
@@ -629,6 +704,14 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         // Metrics: with the dynamic scheduler the slot owns a zeroed integer triple and the last warp out
         // folds it into acc -- one launch.  Static split: the first 24 bytes of the caller's workspace,
         // zeroed before and folded after the kernel.
+        {
+            const Range rd = plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H);
+            const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
+            const Range w1 = plane_range(coef.ptr, coef.pitch, (size_t)W * elem_size(coef.dt), H);
+            // the argument above needs the predecessor to occupy every SM (grid == SM count)
+            const bool early = record_launch(stream, !capturing && pdl_for(capturing) && grid >= di.sms, rd, w0, w1);
+            P.early_loads = (early && !capturing && pdl_for(capturing)) ? 1 : 0;
+        }
         bool separate_finish = false;
         if (partials) {
             P.macc = sched_macc(P.sched);
@@ -656,6 +739,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         return B200DCT_OK;
     }
 
+    forget_stream(stream);
     DirectParams P;
     memset(&P, 0, sizeof(P));
     P.in = in.ptr; P.in_pitch = in.pitch;
@@ -746,6 +830,7 @@ extern "C" int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, 
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
     const bool finv = use_factored_inverse(plan, MODE_RT, (int)dt);
+    forget_stream(s);
     cudaError_t e = dt == B200DCT_F32 ? launch_any_f32(plan->tk, qm, false, P, grid, block, s, pdl_for(capturing))
                                       : launch_any_u8(plan->tk, qm, finv, P, grid, block, s, pdl_for(capturing));
     if (e != cudaSuccess) return (int)e;

@@ -52,6 +52,7 @@ extern "C" int b200dct_roundtrip_rgb(const b200dct_plan *plan, const void *rgb, 
     const bool finv = use_factored_inverse_u8(plan);
     const int qk = (!plan->q_fastdiv || !plan->qc_fastdiv) ? 2
                    : ((plan->q_default && plan->qc_default && plan->mask == ~(uint64_t)0) ? 0 : 1);
+    forget_stream(s);
     cudaError_t e;
     if (qk == 0) e = finv ? launch_rgb<0, true>(P, grid, block, s, pdl) : launch_rgb<0, false>(P, grid, block, s, pdl);
     else if (qk == 1) e = finv ? launch_rgb<1, true>(P, grid, block, s, pdl) : launch_rgb<1, false>(P, grid, block, s, pdl);

@@ -391,6 +391,10 @@ struct TmaParams {
     // coefficients, accumulated with 64-bit integer atomics (order-independent => deterministic)
     unsigned long long *macc;
     double *acc;          // METRICS with the dynamic scheduler: the last warp out adds macc into acc[0..2] and re-zeroes macc
+    // 1: the host has established that nothing this launch READS is written by the launch it may
+    // overlap with (see early_loads_ok in b200dct.cu): tile loads start before griddepcontrol.wait,
+    // every global write (TMA stores, metrics atomics) still waits for the predecessor to complete
+    int early_loads;
     uint32_t bx;          // blocks per image row (lanes of a right-edge tile beyond it hold TMA zero fill, not pixels)
     CommonParams cp;
 };
@@ -623,7 +627,15 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
         }
 #endif
     }
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Only lane 0 ever touches global memory (TMA loads / stores, scheduler and metrics atomics).
+    bool dep_done = !P.early_loads;
+    auto ensure_dep = [&]() { // lane 0, before its first global write
+        if (!dep_done) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            dep_done = true;
+        }
+    };
+    if (!P.early_loads) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (lane == 0 && tile < P.ntiles) issue_load(tile);
     __syncwarp();
 
@@ -677,6 +689,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
+                ensure_dep();
                 if (P.coef_dt == DT_F32) tma_store_3d(map, out_buf, 0, tx * 8, ty * 8);
                 else tma_store_2d(map, out_buf, tx * 256, ty * 8);
                 tma_store_commit();
@@ -729,6 +742,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
+                ensure_dep();
                 if constexpr (PIX == DT_F32) tma_store_3d(&P.out_map, out_buf, 0, tx * 8, ty * 8);
                 else tma_store_2d(&P.out_map, out_buf, tx * 256, ty * 8);
                 tma_store_commit();
@@ -744,12 +758,14 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
             m_nnz += __shfl_xor_sync(0xffffffffu, m_nnz, o);
         }
         if (lane == 0) {
+            ensure_dep();
             atomicAdd(&P.macc[0], (unsigned long long)m_sse);
             atomicAdd(&P.macc[1], (unsigned long long)m_en);
             atomicAdd(&P.macc[2], (unsigned long long)m_nnz);
         }
     }
     if (lane == 0) {
+        ensure_dep(); // a warp without tiles must not let the grid finish ahead of its predecessor's flush
         tma_store_wait_read();
         if (sched) {
             // every warp ends on exactly one losing ticket; the last warp out re-zeroes both counters

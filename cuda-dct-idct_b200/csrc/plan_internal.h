@@ -27,4 +27,5 @@ namespace b200dct {
 void note_launch(int launches, const char *path); // b200dct_last_launch_count / b200dct_last_path of this thread
 bool use_factored_inverse_u8(const b200dct_plan *pl);
 bool pdl_enabled(cudaStream_t s);
+void forget_stream(cudaStream_t s); // a non-TMA kernel of the library was launched on s (see early loads, b200dct.cu)
 }

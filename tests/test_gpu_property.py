@@ -209,3 +209,39 @@ def test_calls_on_a_side_stream(dct, oracle):
         side.synchronize()
         assert np.array_equal(out3.cpu().numpy().view(np.uint32), want.view(np.uint32))
         del busy
+
+
+def test_early_loads_never_break_dependent_call_chains(dct, oracle):
+    """Tile loads of a TMA-family launch may start before its predecessor has completed when the
+    library has established that the predecessor does not write what this launch reads.  Chains in
+    which it DOES (forward -> inverse through one coefficient plane, ping-pong round trips) must stay
+    exact, launch after launch, and independent launches in between must not disturb them."""
+    N = 6144                                   # >= 28 Mpixel: AUTO takes the TMA family, grid = every SM
+    x = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float()
+    y, z, c = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    plan = dct.Plan()
+    want1 = dct.roundtrip(x, plan=plan).clone()
+    want2 = dct.roundtrip(want1, plan=plan).clone()
+    want3 = dct.roundtrip(want2, plan=plan).clone()
+    torch.cuda.synchronize()
+    band = x[:16].cpu().numpy()
+    assert np.array_equal(bits(host(want1[:16])), bits(oracle.roundtrip(band)))
+    for rep in range(25):
+        dct.roundtrip(x, out=y, plan=plan)     # y <- f(x)
+        dct.roundtrip(y, out=z, plan=plan)     # z <- f(y): reads what the previous launch wrote
+        dct.roundtrip(z, out=y, plan=plan)     # y <- f(z): reads AND overwrites across the boundary
+        assert dct.api.last_path() == "tma"
+        dct.forward(x, coef=c, plan=plan)      # split API through one coefficient plane
+        dct.inverse(c, img=z, plan=plan)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int32), want3.view(torch.int32))
+    assert torch.equal(z.view(torch.int32), want1.view(torch.int32))
+    # independent launches (rotating buffers): early loads apply; results identical
+    outs = [torch.empty_like(x) for _ in range(3)]
+    ins = [x, want1, want2]
+    for rep in range(10):
+        for i in range(3):
+            dct.roundtrip(ins[i], out=outs[i], plan=plan)
+    torch.cuda.synchronize()
+    for o, w in zip(outs, (want1, want2, want3)):
+        assert torch.equal(o.view(torch.int32), w.view(torch.int32))
