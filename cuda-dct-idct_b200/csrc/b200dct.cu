@@ -458,10 +458,11 @@ unsigned long long *sched_macc(const uint32_t *slot)
 //   * the relaxation only ever applies to the immediately preceding kernel of the stream, and only if
 //     that kernel triggers launch_dependents -- i.e. one of this library's; anything else the caller
 //     enqueues in between (copies, other kernels) restores full stream order by itself;
-//   * when that predecessor is a persistent TMA-family launch that fills the machine (one CTA on every SM, more than half of an SM's
-//     registers or shared memory, so a successor CTA starts only where a predecessor CTA has EXITED,
-//     which it cannot do before having passed its own wait), everything older than the predecessor
-//     is complete by the time a successor CTA runs: only the predecessor's writes matter;
+//   * when that predecessor is a persistent TMA-family launch that fills the machine (a CTA on every SM)
+//     and both launches take more than half of an SM's shared memory (so they can never share an SM),
+//     a successor CTA starts only where a predecessor CTA has EXITED, which it cannot do before
+//     having passed its own wait: everything older than the predecessor is complete by the time a
+//     successor CTA runs, and only the predecessor's writes matter;
 //   * so: predecessor on this stream = TMA family, and [input plane] disjoint from its output /
 //     coefficient planes  =>  early_loads.  Every other launch of the library clears the record.
 // Not under stream capture.  env B200DCT_EARLY_LOADS=0 disables (A/B).
@@ -708,8 +709,10 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
             const Range rd = plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H);
             const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
             const Range w1 = plane_range(coef.ptr, coef.pitch, (size_t)W * elem_size(coef.dt), H);
-            // the argument above needs the predecessor to occupy every SM (grid == SM count)
-            const bool early = record_launch(stream, !capturing && pdl_for(capturing) && grid >= di.sms, rd, w0, w1);
+            // the argument above needs the predecessor to occupy every SM (grid == SM count) and neither
+            // launch to fit beside the other on one SM: both take more than half of its shared memory
+            const bool heavy = smem > (size_t)(di.smem_optin / 2) + 1024;
+            const bool early = record_launch(stream, !capturing && pdl_for(capturing) && grid >= di.sms && heavy, rd, w0, w1);
             P.early_loads = (early && !capturing && pdl_for(capturing)) ? 1 : 0;
         }
         bool separate_finish = false;
