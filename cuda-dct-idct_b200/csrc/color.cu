@@ -7,8 +7,8 @@
 
 using namespace b200dct;
 
-template <int QK, bool FINV>
-static cudaError_t launch_rgb(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+template <int QK, bool FINV, bool ZZ>
+static cudaError_t launch_rgb3(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
@@ -19,7 +19,12 @@ static cudaError_t launch_rgb(const RgbParams &P, dim3 grid, dim3 block, cudaStr
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_rgb<QK, FINV>, P);
+    return cudaLaunchKernelEx(&cfg, k_rgb<QK, FINV, ZZ>, P);
+}
+template <int QK, bool FINV>
+static cudaError_t launch_rgb(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+{
+    return P.zz ? launch_rgb3<QK, FINV, true>(P, grid, block, s, pdl) : launch_rgb3<QK, FINV, false>(P, grid, block, s, pdl);
 }
 
 extern "C" int b200dct_roundtrip_rgb(const b200dct_plan *plan, const void *rgb, size_t in_pitch, void *out,
@@ -43,15 +48,18 @@ extern "C" int b200dct_roundtrip_rgb(const b200dct_plan *plan, const void *rgb, 
     P.out = out; P.out_pitch = out_pitch;
     P.zz = zz3_or_null; P.zz_plane = zz_plane_bytes; P.zz_pitch = (size_t)(W / 8) * 128;
     P.bx = W / 8; P.by = H / 8;
-    P.q = plan->cp.q;
-    P.qc = plan->qc;
+    for (int k = 0; k < 64; k++) {
+        P.t[0].rd[k] = make_float2(plan->cp.q.rcp[k], plan->cp.q.d[k]);
+        P.t[0].keep[k] = plan->cp.q.keep[k];
+        P.t[1].rd[k] = make_float2(plan->qc.rcp[k], plan->qc.d[k]);
+        P.t[1].keep[k] = plan->qc.keep[k];
+    }
     dim3 block(32, 4), grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32));
     if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
     cudaStream_t s = (cudaStream_t)stream;
     const bool pdl = pdl_enabled(s);
     const bool finv = use_factored_inverse_u8(plan);
-    const int qk = (!plan->q_fastdiv || !plan->qc_fastdiv) ? 2
-                   : ((plan->q_default && plan->qc_default && plan->mask == ~(uint64_t)0) ? 0 : 1);
+    const int qk = (!plan->q_fastdiv || !plan->qc_fastdiv) ? 2 : (plan->mask == ~(uint64_t)0 ? 0 : 1);
     forget_stream(s);
     cudaError_t e;
     if (qk == 0) e = finv ? launch_rgb<0, true>(P, grid, block, s, pdl) : launch_rgb<0, false>(P, grid, block, s, pdl);

@@ -43,23 +43,31 @@ __host__ __device__ constexpr float jpeg_q_chroma(int k)
         99, 99, 99, 99, 99, 99, 99, 99};
     return q[k];
 }
-struct QImmChroma {
-    static constexpr bool masked = false;
-    static constexpr bool fastdiv = true;
-    __device__ __forceinline__ float neg_d(int k) const { return -jpeg_q_chroma(k); }
-    __device__ __forceinline__ float rcp(int k) const { return 1.0f / jpeg_q_chroma(k); }
-    __device__ __forceinline__ float d(int k) const { return jpeg_q_chroma(k); }
-    __device__ __forceinline__ uint32_t keep(int) const { return 0xffffffffu; }
+// Quantiser tables of the two plane kinds as {1/Q, Q} pairs: the plane loop below is ONE copy of the
+// transform code for Y, Cb and Cr, so the table entries cannot be immediates or fixed constant-bank
+// operands; one 64-bit constant load per coefficient fetches both values (-Q is an operand modifier).
+struct PlaneTables {
+    float2 rd[64];     // {RN(1/Q), Q}
+    uint32_t keep[64]; // 0xffffffff kept / 0 dropped
 };
-
 struct RgbParams {
     const void *in;  // interleaved RGB u8, 8-byte aligned rows
     void *out;
     void *zz;        // optional: three block-major zig-zag int16 streams (Y, Cb, Cr), zz_plane bytes apart
     size_t in_pitch, out_pitch, zz_plane, zz_pitch; // bytes; zz_pitch = bytes per block-row of one stream
     int bx, by;
-    QuantTables q;   // luminance
-    QuantTables qc;  // chrominance
+    PlaneTables t[2]; // [0] luminance, [1] chrominance
+};
+template <bool MASKED, bool FASTDIV>
+struct QPlane {
+    static constexpr bool masked = MASKED;
+    static constexpr bool fastdiv = FASTDIV;
+    const PlaneTables &t;
+    __device__ __forceinline__ explicit QPlane(const PlaneTables &tt) : t(tt) {}
+    __device__ __forceinline__ float rcp(int k) const { return t.rd[k].x; }
+    __device__ __forceinline__ float d(int k) const { return t.rd[k].y; }
+    __device__ __forceinline__ float neg_d(int k) const { return -t.rd[k].y; }
+    __device__ __forceinline__ uint32_t keep(int k) const { return t.keep[k]; }
 };
 
 constexpr float RGB_MAGIC = 12582912.0f; // 1.5 * 2^23: x + MAGIC in RM mode = MAGIC + floor(x) for |x| < 2^22
@@ -73,11 +81,29 @@ __device__ __forceinline__ float row_byte(const uint32_t (&w)[6])
 {
     return u8_to_float(w[J >> 2], J & 3);
 }
+// the low mantissa bytes of eight MAGIC-biased floats as eight packed bytes
+__device__ __forceinline__ uint2 pack_magic_bytes(const float (&v)[8])
+{
+    uint2 o;
+    o.x = __byte_perm(__byte_perm(__float_as_uint(v[0]), __float_as_uint(v[1]), 0x0040), __byte_perm(__float_as_uint(v[2]), __float_as_uint(v[3]), 0x0040), 0x5410);
+    o.y = __byte_perm(__byte_perm(__float_as_uint(v[4]), __float_as_uint(v[5]), 0x0040), __byte_perm(__float_as_uint(v[6]), __float_as_uint(v[7]), 0x0040), 0x5410);
+    return o;
+}
 
-// QK: 0 immediates (default tables, all coefficients kept), 1 parameter tables + exact fast division + mask,
-//     2 parameter tables + __fdiv_rn + mask
-template <int QK, bool FINV>
-__global__ void __launch_bounds__(128, 4) k_rgb(const __grid_constant__ RgbParams P)
+// Code size matters here: the L1.5 instruction cache holds 32 KiB, and the first version of this
+// kernel (Y transformed by its own copy of the code with immediate tables, both colour conversions
+// unrolled over the 8 rows: 5232 instructions = 84 KiB, executed once per thread) spent 5 of 6 issue
+// slots waiting for instructions (ncu: stall no_instruction 5.2 per issue, 346 us per 8192^2 image).
+// Now the three planes run through ONE copy of the transform in a loop, and the two conversions are
+// one row of code each, looped over the rows through shared memory.
+// QK: 0 all coefficients kept, exact fast division; 1 mask + exact fast division; 2 mask + __fdiv_rn
+#ifndef B200DCT_RGB_MIN_BLOCKS
+#define B200DCT_RGB_MIN_BLOCKS 5
+#endif
+// ZZ: also emit the three zig-zag coefficient streams (its own instantiation: 150 instructions the
+// default kernel does not have to carry through the instruction cache)
+template <int QK, bool FINV, bool ZZ>
+__global__ void __launch_bounds__(128, B200DCT_RGB_MIN_BLOCKS) k_rgb(const __grid_constant__ RgbParams P)
 {
     // [plane][row][thread] 8-byte slots: a warp's access is 256 contiguous bytes (conflict-free)
     __shared__ uint2 park[3][8][128];
@@ -88,72 +114,51 @@ __global__ void __launch_bounds__(128, 4) k_rgb(const __grid_constant__ RgbParam
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    float2 p[8][4];
-    // ---- load + RGB -> YCbCr (jccolor.c rgb_ycc_convert)
+    // ---- load + RGB -> YCbCr (jccolor.c rgb_ycc_convert), one row per iteration
     {
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 24;
-        sfor<8>([&](auto r) {
-            const uint2 *row = reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch);
+#pragma unroll 1
+        for (int r = 0; r < 8; r++) {
+            const uint2 *row = reinterpret_cast<const uint2 *>(src + (size_t)r * P.in_pitch);
             const uint2 a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
             const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
             float yv[8], cbv[8], crv[8];
             sfor<8>([&](auto k) {
                 const float R = row_byte<3 * IC(k)>(w), G = row_byte<3 * IC(k) + 1>(w), B = row_byte<3 * IC(k) + 2>(w);
-                // every partial sum is an integer multiple of 2^-16 below 2^8: exact
-                const float y = __fmaf_rn(R, B200_FIX(0.29900), __fmaf_rn(G, B200_FIX(0.58700), __fmaf_rn(B, B200_FIX(0.11400), 0.5f)));
-                const float cb = __fmaf_rn(R, -B200_FIX(0.16874), __fmaf_rn(G, -B200_FIX(0.33126), __fmaf_rn(B, 0.5f, 128.0f + 32767.0f / 65536.0f)));
-                const float cr = __fmaf_rn(R, 0.5f, __fmaf_rn(G, -B200_FIX(0.41869), __fmaf_rn(B, -B200_FIX(0.08131), 128.0f + 32767.0f / 65536.0f)));
-                yv[IC(k)] = floor_magic(y) - (RGB_MAGIC + 128.0f); // sample - 128: the transform's input (sub_matrix_scalar)
-                cbv[IC(k)] = floor_magic(cb);                      // low mantissa byte = the sample
-                crv[IC(k)] = floor_magic(cr);
+                // every partial sum is an integer multiple of 2^-16 below 2^8: exact; the low mantissa byte
+                // of MAGIC + floor(.) is the sample
+                yv[IC(k)] = floor_magic(__fmaf_rn(R, B200_FIX(0.29900), __fmaf_rn(G, B200_FIX(0.58700), __fmaf_rn(B, B200_FIX(0.11400), 0.5f))));
+                cbv[IC(k)] = floor_magic(__fmaf_rn(R, -B200_FIX(0.16874), __fmaf_rn(G, -B200_FIX(0.33126), __fmaf_rn(B, 0.5f, 128.0f + 32767.0f / 65536.0f))));
+                crv[IC(k)] = floor_magic(__fmaf_rn(R, 0.5f, __fmaf_rn(G, -B200_FIX(0.41869), __fmaf_rn(B, -B200_FIX(0.08131), 128.0f + 32767.0f / 65536.0f))));
             });
-            sfor<4>([&](auto j) { p[IC(r)][IC(j)] = make_float2(yv[2 * IC(j)], yv[2 * IC(j) + 1]); });
-            auto pack = [](const float (&v)[8]) {
-                uint2 o;
-                o.x = __byte_perm(__byte_perm(__float_as_uint(v[0]), __float_as_uint(v[1]), 0x0040), __byte_perm(__float_as_uint(v[2]), __float_as_uint(v[3]), 0x0040), 0x5410);
-                o.y = __byte_perm(__byte_perm(__float_as_uint(v[4]), __float_as_uint(v[5]), 0x0040), __byte_perm(__float_as_uint(v[6]), __float_as_uint(v[7]), 0x0040), 0x5410);
-                return o;
-            };
-            park[1][IC(r)][tid] = pack(cbv);
-            park[2][IC(r)][tid] = pack(crv);
-        });
+            park[0][r][tid] = pack_magic_bytes(yv);
+            park[1][r][tid] = pack_magic_bytes(cbv);
+            park[2][r][tid] = pack_magic_bytes(crv);
+        }
     }
 
-    auto emit = [&](int plane, float2 (&c)[8][4]) {
-        if (P.zz) st_block_zigzag((char *)P.zz + (size_t)plane * P.zz_plane + (size_t)by * P.zz_pitch + (size_t)bxi * 128, c);
-    };
-    auto round_trip = [&](auto chroma, int plane) {
-        constexpr bool CH = decltype(chroma)::value;
-        auto run = [&](const auto &qp) {
-            forward_block<KeepAll>(p, HaweelT<false, true>{}, qp);
-            emit(plane, p);
-            if constexpr (FINV) {
-                inverse_block_fast<true>(p, qp);
-            } else {
-                inverse_block<KeepAll>(p, HaweelT<true, true>{}, qp);
-                sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); }); // add_matrix_scalar, utils_kernels.cu:29
-            }
-        };
-        if constexpr (QK == 0) {
-            if constexpr (CH) run(QImmChroma{});
-            else run(QImm{});
+    // ---- the three planes through one copy of the reference's u8 pipeline
+#pragma unroll 1
+    for (int plane = 0; plane < 3; plane++) {
+        float2 p[8][4];
+        sfor<8>([&](auto r) { unpack_u8_shifted(park[plane][IC(r)][tid], p[IC(r)]); }); // convertToFloat + sub_matrix_scalar
+        const QPlane<QK != 0, QK != 2> qp(P.t[plane != 0]);
+        forward_block<KeepAll>(p, HaweelT<false, true>{}, qp);
+        if constexpr (ZZ) st_block_zigzag((char *)P.zz + (size_t)plane * P.zz_plane + (size_t)by * P.zz_pitch + (size_t)bxi * 128, p);
+        if constexpr (FINV) {
+            inverse_block_fast<true>(p, qp);
         } else {
-            run(QParam<true, QK == 1>(CH ? P.qc : P.q));
+            inverse_block<KeepAll>(p, HaweelT<true, true>{}, qp);
+            sfor<8>([&](auto r) { shift_row(p[IC(r)], 128.0f); }); // add_matrix_scalar, utils_kernels.cu:29
         }
         sfor<8>([&](auto r) { park[plane][IC(r)][tid] = pack_u8_row(p[IC(r)]); }); // convertToUnsignedChar, utils.cu:21
-    };
-
-    round_trip(std::false_type{}, 0);
-#pragma unroll 1
-    for (int plane = 1; plane < 3; plane++) { // Cb, Cr: same code, run twice
-        sfor<8>([&](auto r) { unpack_u8_shifted(park[plane][IC(r)][tid], p[IC(r)]); });
-        round_trip(std::true_type{}, plane);
     }
 
-    // ---- YCbCr -> RGB (jdcolor.c ycc_rgb_convert) + store
+    // ---- YCbCr -> RGB (jdcolor.c ycc_rgb_convert) + store, one row per iteration
     char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 24;
-    sfor<8>([&](auto r) {
-        const uint2 yw = park[0][IC(r)][tid], bw = park[1][IC(r)][tid], rw = park[2][IC(r)][tid];
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        const uint2 yw = park[0][r][tid], bw = park[1][r][tid], rw = park[2][r][tid];
         float o[24];
         sfor<8>([&](auto k) {
             const uint32_t ys = IC(k) < 4 ? yw.x : yw.y, bs = IC(k) < 4 ? bw.x : bw.y, rs = IC(k) < 4 ? rw.x : rw.y;
@@ -163,11 +168,11 @@ __global__ void __launch_bounds__(128, 4) k_rgb(const __grid_constant__ RgbParam
             o[3 * IC(k) + 1] = floor_magic(__fmaf_rn(cr, -B200_FIX(0.71414), __fmaf_rn(cb, -B200_FIX(0.34414), 0.5f))) + ym;
             o[3 * IC(k) + 2] = floor_magic(__fmaf_rn(cb, B200_FIX(1.77200), 0.5f)) + ym;
         });
-        uint2 *row = reinterpret_cast<uint2 *>(dst + IC(r) * P.out_pitch);
+        uint2 *row = reinterpret_cast<uint2 *>(dst + (size_t)r * P.out_pitch);
         row[0] = make_uint2(pack4_u8(o[0], o[1], o[2], o[3]), pack4_u8(o[4], o[5], o[6], o[7]));       // range_limit = saturation
         row[1] = make_uint2(pack4_u8(o[8], o[9], o[10], o[11]), pack4_u8(o[12], o[13], o[14], o[15]));
         row[2] = make_uint2(pack4_u8(o[16], o[17], o[18], o[19]), pack4_u8(o[20], o[21], o[22], o[23]));
-    });
+    }
 }
 
 } // namespace b200dct
