@@ -351,11 +351,11 @@ static bool make_map(CUtensorMap *map, const void *ptr, int dt, size_t pitch, in
     encode_tiled_fn enc = get_encode();
     if (!enc) return false;
     CUresult r;
-    static int promo_env = -1; // developer knob: B200DCT_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B
-    if (promo_env < 0) {
+    // developer knob: B200DCT_TMA_L2PROMO = 0 none, 1 64B, 2 128B, 3 256B (read once; magic statics are thread-safe)
+    static const int promo_env = [] {
         const char *e = getenv("B200DCT_TMA_L2PROMO");
-        promo_env = (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 3;
-    }
+        return (e && atoi(e) >= 0 && atoi(e) <= 3) ? atoi(e) : 3;
+    }();
     const CUtensorMapL2promotion promo = (CUtensorMapL2promotion)promo_env;
     if (dt == DT_F32) {
         // {32 floats, W/32 segments, H rows}; box = 8 rows x 8 segments x 128 B, 128B swizzle
@@ -491,12 +491,11 @@ Range plane_range(const void *p, size_t pitch, size_t row_bytes, int H)
 bool disjoint(const Range &a, const Range &b) { return a.hi <= b.lo || b.hi <= a.lo || a.lo == a.hi || b.lo == b.hi; }
 bool early_loads_enabled()
 {
-    static int v = -1;
-    if (v < 0) {
+    static const bool v = [] {
         const char *p = getenv("B200DCT_EARLY_LOADS");
-        v = (p && atoi(p) == 0) ? 0 : 1;
-    }
-    return v == 1;
+        return !(p && atoi(p) == 0);
+    }();
+    return v;
 }
 // Returns whether a TMA launch reading `rd` on `stream` may load early, and records this launch.
 bool record_launch(cudaStream_t stream, bool tma, const Range &rd, const Range &w0, const Range &w1)
@@ -534,23 +533,21 @@ static int tma_max_run = 2;                       // env B200DCT_TMA_RUN: longes
 // back to back: 83.9 -> 81.8 us (profiles/r01_pdl.txt).
 static bool use_pdl()
 {
-    static int v = -1;
-    if (v < 0) {
+    static const bool v = [] {
         const char *p = getenv("B200DCT_PDL");
-        v = (p && atoi(p) == 0) ? 0 : 1;
-    }
-    return v == 1;
+        return !(p && atoi(p) == 0);
+    }();
+    return v;
 }
 // Under stream capture the attribute becomes a programmatic edge of the graph (CUDA >= 12.3);
 // off unless B200DCT_PDL_CAPTURE=1 (experiment).
 static bool pdl_for(bool capturing)
 {
-    static int cap = -1;
-    if (cap < 0) {
+    static const bool cap = [] {
         const char *p = getenv("B200DCT_PDL_CAPTURE");
-        cap = (p && atoi(p) == 1) ? 1 : 0;
-    }
-    return use_pdl() && (!capturing || cap == 1);
+        return p && atoi(p) == 1;
+    }();
+    return use_pdl() && (!capturing || cap);
 }
 namespace b200dct {
 bool use_factored_inverse_u8(const b200dct_plan *pl) { return use_factored_inverse(pl, MODE_RT, DT_U8); }
@@ -564,12 +561,11 @@ bool pdl_enabled(cudaStream_t s)
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
 static bool compiled_masks() // env B200DCT_COMPILED_MASKS=0: retained-coefficient masks as runtime data only (A/B)
 {
-    static int v = -1;
-    if (v < 0) {
+    static const bool v = [] {
         const char *p = getenv("B200DCT_COMPILED_MASKS");
-        v = (p && atoi(p) == 0) ? 0 : 1;
-    }
-    return v == 1;
+        return !(p && atoi(p) == 0);
+    }();
+    return v;
 }
 
 static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,

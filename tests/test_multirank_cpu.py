@@ -38,6 +38,12 @@ def _worker(rank, world, port, H, W, q):
     m.dist.barrier()
     slowest = m.dist.max_over_ranks(10.0 + rank)      # rank-dependent "time"
     total = m.dist.sum_over_ranks(float((r1 - r0) * W))
+    per_rank = m.dist.all_ranks(10.0 + rank)          # bench.py's per-rank timing diagnostics
+    assert per_rank == [10.0 + i for i in range(world)]
+    # bench.py's parity_all_ranks: every rank checks its own stripe, the failure flags are summed
+    ok = np.array_equal(mine.view(np.uint32), o.roundtrip(img)[r0:r1].view(np.uint32))
+    assert m.dist.sum_over_ranks(0.0 if ok else 1.0) == 0.0
+    assert m.dist.sum_over_ranks(1.0 if rank == 1 else 0.0) == 1.0   # one failing rank is seen by all
     full = m.dist.gather_stripes(torch.from_numpy(mine), H, dst=0)
     if rank == 0:
         q.put((slowest, total, full.numpy()))
