@@ -498,11 +498,12 @@ bool early_loads_enabled()
     return v;
 }
 // Returns whether a TMA launch reading `rd` on `stream` may load early, and records this launch.
-bool record_launch(cudaStream_t stream, bool tma, const Range &rd, const Range &w0, const Range &w1)
+// The caller holds g_last_mu and keeps it until the kernel has been enqueued: the record order must be
+// the stream order even when several host threads launch on one stream.
+bool record_launch_locked(cudaStream_t stream, bool tma, const Range &rd, const Range &w0, const Range &w1)
 {
     int dev = -1;
     if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    std::lock_guard<std::mutex> lk(g_last_mu);
     LastLaunch *e = nullptr, *freeslot = nullptr;
     for (auto &x : g_last) {
         if (x.dev == dev && x.stream == stream) e = &x;
@@ -520,7 +521,11 @@ bool record_launch(cudaStream_t stream, bool tma, const Range &rd, const Range &
 }
 } // namespace
 namespace b200dct {
-void forget_stream(cudaStream_t s) { record_launch(s, false, Range{}, Range{}, Range{}); }
+void forget_stream(cudaStream_t s)
+{
+    std::lock_guard<std::mutex> lk(g_last_mu);
+    record_launch_locked(s, false, Range{}, Range{}, Range{});
+}
 }
 
 static bool tma_dynamic = true; // env B200DCT_TMA_STATIC=1 forces the static tile split
@@ -701,6 +706,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         // Metrics: with the dynamic scheduler the slot owns a zeroed integer triple and the last warp out
         // folds it into acc -- one launch.  Static split: the first 24 bytes of the caller's workspace,
         // zeroed before and folded after the kernel.
+        std::unique_lock<std::mutex> launch_order(g_last_mu); // held until this kernel is in the stream
         {
             const Range rd = plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H);
             const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
@@ -708,7 +714,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
             // the argument above needs the predecessor to occupy every SM (grid == SM count) and neither
             // launch to fit beside the other on one SM: both take more than half of its shared memory
             const bool heavy = smem > (size_t)(di.smem_optin / 2) + 1024;
-            const bool early = record_launch(stream, !capturing && pdl_for(capturing) && grid >= di.sms && heavy, rd, w0, w1);
+            const bool early = record_launch_locked(stream, !capturing && pdl_for(capturing) && grid >= di.sms && heavy, rd, w0, w1);
             P.early_loads = (early && !capturing && pdl_for(capturing)) ? 1 : 0;
         }
         bool separate_finish = false;
@@ -726,6 +732,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         cudaError_t e = kmask
                             ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing))
                             : launch_tma(pl->tk, mode, qm, pix, finv, P, grid, nw * 32, smem, stream, pdl_for(capturing) && !separate_finish);
+        launch_order.unlock();
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
         if (separate_finish) {
