@@ -245,3 +245,60 @@ def test_early_loads_never_break_dependent_call_chains(dct, oracle):
     torch.cuda.synchronize()
     for o, w in zip(outs, (want1, want2, want3)):
         assert torch.equal(o.view(torch.int32), w.view(torch.int32))
+
+
+def test_early_loads_with_threads_and_streams(dct, oracle):
+    """Early tile loads are decided per (device, stream) under one lock with the launch itself: two
+    host threads hammering ONE stream with dependent pairs, and two streams chained by events, stay
+    exact."""
+    import threading
+
+    N = 6144
+    x = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float()
+    plan = dct.Plan()
+    want1 = dct.roundtrip(x, plan=plan).clone()
+    want2 = dct.roundtrip(want1, plan=plan).clone()
+    torch.cuda.synchronize()
+    # (1) one stream, two threads, each running its own dependent chain x -> a -> b
+    s = torch.cuda.Stream()
+    bufs = [(torch.empty_like(x), torch.empty_like(x)) for _ in range(2)]
+    errs = []
+
+    def work(i):
+        try:
+            a, b = bufs[i]
+            for _ in range(15):
+                dct.roundtrip(x, out=a, plan=plan, stream=s)
+                dct.roundtrip(a, out=b, plan=plan, stream=s)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    s.synchronize()
+    assert not errs
+    for a, b in bufs:
+        assert torch.equal(a.view(torch.int32), want1.view(torch.int32))
+        assert torch.equal(b.view(torch.int32), want2.view(torch.int32))
+    # (2) two streams chained by events: s2 consumes what s1 produced, s1 keeps producing into the other buffer
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    prod = [torch.empty_like(x) for _ in range(2)]
+    cons = [torch.empty_like(x) for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    for it in range(12):
+        k = it % 2
+        if it >= 2:
+            s1.wait_event(freed[k])
+        dct.roundtrip(x, out=prod[k], plan=plan, stream=s1)
+        done[k].record(s1)
+        s2.wait_event(done[k])
+        dct.roundtrip(prod[k], out=cons[k], plan=plan, stream=s2)
+        freed[k].record(s2)
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert torch.equal(prod[k].view(torch.int32), want1.view(torch.int32))
+        assert torch.equal(cons[k].view(torch.int32), want2.view(torch.int32))
