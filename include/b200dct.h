@@ -202,7 +202,9 @@ int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, b200dct_dty
  * README.md:67-68 of the reference) and the coefficient density need no second pass over the
  * images.  Per-CTA partial sums go to `workspace` (device, >= b200dct_metrics_workspace_bytes,
  * caller-owned, 8-byte aligned) and are reduced in a fixed order: results are deterministic,
- * exact for u8 images.  `out` must not alias `img`.  Runs on the direct kernel family. */
+ * exact for u8 images.  `out` must not alias `img`.  Large f32 images of Haweel's T run the TMA family's
+ * metrics kernel (the error is taken from the input tile in shared memory, sums accumulate as 64-bit
+ * fixed point: still deterministic); everything else the direct family's. */
 size_t b200dct_metrics_workspace_bytes(int H, int W);
 int b200dct_roundtrip_metrics(const b200dct_plan *plan,
                               const void *img, b200dct_dtype in_dt, size_t in_pitch,
