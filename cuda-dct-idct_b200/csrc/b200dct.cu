@@ -604,10 +604,12 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // profiles/r01_small_sizes.txt): 256^2 3.4 vs 6.7 us, 2048^2 7.9 vs 9.7, 4096^2 22.9 vs 24.6,
     // 5120^2 34.9 vs 35.0, 6144^2 48.9 vs 48.0, 8192^2 83.8 vs 81.8.
     const bool big = (unsigned long long)H * (unsigned long long)W >= (28ull << 20);
-    // Symmetric dense T (16+16 FMA/px): the direct family wins up to 12288^2 (84.6 vs 88.0 us at 8192^2,
-    // 187.7 vs 189.0 at 12288^2), the persistent TMA kernel beyond (16384^2: 321.9 vs 333.9 us;
-    // profiles/r02_dense_paths.txt).  Ordered-chain dense kernels stay on the direct family.
-    const bool huge = (unsigned long long)H * (unsigned long long)W >= (200ull << 20);
+    // Symmetric dense T (16+16 FMA/px).  Before early tile loads the direct family won up to 12288^2
+    // (84.6 vs 88.0 us at 8192^2, 187.7 vs 189.0 at 12288^2) and the persistent TMA kernel beyond
+    // (16384^2: 321.9 vs 333.9 us); with early loads across launch boundaries the TMA family wins from
+    // 8192^2 on: 80.2 vs 84.7 us, 16384^2 314.7 vs 330.9 us (profiles/r02_dense_paths.txt).  Ordered-chain
+    // dense kernels stay on the direct family.
+    const bool huge = (unsigned long long)H * (unsigned long long)W >= (64ull << 20);
     const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big) ||
                             (bytes_per_px >= 4 && pl->tk == TK_DENSE_SYM && huge);
     // Under stream capture the launch takes a ticket-counter pair of its own (see SchedRing); when
