@@ -181,9 +181,23 @@ def test_cublas2_mismatch_counts_at_larger_sizes(oracle, dct, N):
         b = dct.metrics(u8, ref_rec.clamp(0, 255).to(torch.uint8))
         assert a[0] == pytest.approx(b[0], rel=1e-3) and a[1] == pytest.approx(b[1], rel=1e-3)
         assert int((rec.clamp(0, 255).to(torch.uint8).int() - ref_rec.clamp(0, 255).to(torch.uint8).int()).abs().max()) <= 1
+    # the tensor-core arm (fused round trip only): same criterion against the live cuBLAS result
+    cm = torch.empty(N, N, device="cuda")
+    om = dct.roundtrip(dev(img), coef=cm, plan=dct.Plan(T=Tm, dense=dct.api.DENSE_MMA))
+    assert dct.api.last_path() == "mma"
+    counts["mma"] = int((cm != keep).sum())
+    assert float((cm - keep).abs().max()) <= 1
+    u8 = dev(img).to(torch.uint8)
+    a = dct.metrics(u8, om.clamp(0, 255).to(torch.uint8))
+    b = dct.metrics(u8, ref_rec.clamp(0, 255).to(torch.uint8))
+    assert a[0] == pytest.approx(b[0], rel=1e-3) and a[1] == pytest.approx(b[1], rel=1e-3)
+    same = (cm == keep).view(N // 8, 8, N // 8, 8).all(dim=3).all(dim=1)                # blocks with identical coefficients
+    pd = (om - ref_rec).abs().view(N // 8, 8, N // 8, 8).amax(dim=3).amax(dim=1)
+    assert float(pd[same].max()) < 2e-3
     print(f"[cublas2/dct2 {N}^2] coefficient mismatches vs live cuBLAS: chain {counts['chain']}, "
-          f"even/odd {counts['symmetric']} of {N * N}")
+          f"even/odd {counts['symmetric']}, tensor-core arm {counts['mma']} of {N * N}")
     assert counts["symmetric"] <= max(2 * counts["chain"], 1e-3 * N * N)
+    assert counts["mma"] <= 2e-3 * N * N
 
 
 def test_committed_reference_fixtures_match_live_reference(oracle):
