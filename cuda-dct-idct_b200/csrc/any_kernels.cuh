@@ -110,6 +110,13 @@ __device__ __forceinline__ uint32_t ldg_u32(uintptr_t a)
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(a));
     return v;
 }
+// predicated form: lanes with p == false issue no access at all (and get 0)
+__device__ __forceinline__ uint32_t ldg_u32_if(uintptr_t a, bool p)
+{
+    uint32_t v;
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\nmov.u32 %0, 0;\n@q ld.global.u32 %0, [%1];\n}" : "=r"(v) : "l"(a), "r"((uint32_t)p));
+    return v;
+}
 __device__ __forceinline__ uint32_t ldg_u8(uintptr_t a)
 {
     uint32_t v;
@@ -136,17 +143,17 @@ __global__ void __launch_bounds__(128, 5) k_any_u8(const __grid_constant__ AnyPa
     // All loads of the block are issued before anything waits for one of them: the main path is
     // branch-free (a per-row branch, even a warp-uniform one, keeps ptxas from hoisting the next
     // row's loads over it -- measured: 8 serialised memory round trips per warp, 101 us at 8191^2).
-    // Lanes without a whole block inside the image read the row's first word instead (valid memory).
+    // Lanes without a whole block inside the image issue no access (predicated loads, not branches).
     float2 p[8][4];
     uint2 w[8];
     const uintptr_t in0 = (uintptr_t)P.in;
     sfor<8>([&](auto r) {
         const long long y = y0 + IC(r) < P.H ? y0 + IC(r) : P.H - 1;
-        const uintptr_t a = in0 + (size_t)y * P.in_pitch + (full ? (size_t)xb : 0);
+        const uintptr_t a = in0 + (size_t)y * P.in_pitch + (size_t)xb;
         const uintptr_t wa = a & ~(uintptr_t)3;
         const unsigned sh = (unsigned)(a & 3) * 8;
-        const uint32_t w0 = ldg_u32(wa), w1 = ldg_u32(wa + 4);
-        const uint32_t w2 = ldg_u32(wa + (sh ? 8 : 4)); // the third word holds own bytes iff sh != 0; never read past them
+        const uint32_t w0 = ldg_u32_if(wa, full), w1 = ldg_u32_if(wa + 4, full);
+        const uint32_t w2 = ldg_u32_if(wa + (sh ? 8 : 4), full); // the third word holds own bytes iff sh != 0; never read past them
         w[IC(r)].x = __funnelshift_r(w0, w1, sh);
         w[IC(r)].y = __funnelshift_r(w1, w2, sh);
     });
