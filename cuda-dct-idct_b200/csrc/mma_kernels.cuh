@@ -100,15 +100,19 @@ __global__ void __launch_bounds__(128, 8) k_mma(const __grid_constant__ MmaParam
     const char *src0 = (const char *)P.in + row_a * P.in_pitch + col * 4;
     char *dst0 = (char *)P.out + row_a * P.out_pitch + col * 4;
     char *cf0 = P.coef ? (char *)P.coef + row_a * P.coef_pitch + col * 4 : nullptr;
-    constexpr int U = 8; // independent blocks in flight per warp
-    for (int b = 0; b < nb; b += U) {
-        float x0[U], x1[U];
+    constexpr int U = 8; // independent blocks per batch; the next batch's loads are in flight while this one computes
+    float x0[U], x1[U], n0[U], n1[U];
+    auto load_batch = [&](int b, float (&a0)[U], float (&a1)[U]) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const bool ok = b + u < nb;
-            x0[u] = ok ? *reinterpret_cast<const float *>(src0 + (size_t)(b + u) * 32) : 0.0f;
-            x1[u] = ok ? *reinterpret_cast<const float *>(src0 + P.in_pitch + (size_t)(b + u) * 32) : 0.0f;
+            a0[u] = ok ? __ldg(reinterpret_cast<const float *>(src0 + (size_t)(b + u) * 32)) : 0.0f;
+            a1[u] = ok ? __ldg(reinterpret_cast<const float *>(src0 + P.in_pitch + (size_t)(b + u) * 32)) : 0.0f;
         }
+    };
+    load_batch(0, x0, x1);
+    for (int b = 0; b < nb; b += U) {
+        if (b + U < nb) load_batch(b + U, n0, n1);
 #pragma unroll
         for (int u = 0; u < U; u++) {
             float v0 = x0[u] - 128.0f, v1 = x1[u] - 128.0f; // sub_matrix_scalar, utils_kernels.cu:16
@@ -124,15 +128,15 @@ __global__ void __launch_bounds__(128, 8) k_mma(const __grid_constant__ MmaParam
             v1 *= d1;
             mma_pass(ainv, v0, v1, v0, v1);                  // M2 = T^T.D       lane: M2[g][2q], M2[g][2q+1]
             mma_pass(ainv, v0, v1, v0, v1);                  // R^T = T^T.M2^T   lane: R[2q][g], R[2q+1][g]
-            x0[u] = v0 + 128.0f;                             // add_matrix_scalar, utils_kernels.cu:29
-            x1[u] = v1 + 128.0f;
+            if (b + u < nb) {
+                *reinterpret_cast<float *>(dst0 + (size_t)(b + u) * 32) = v0 + 128.0f; // add_matrix_scalar, utils_kernels.cu:29
+                *reinterpret_cast<float *>(dst0 + P.out_pitch + (size_t)(b + u) * 32) = v1 + 128.0f;
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            if (b + u < nb) {
-                *reinterpret_cast<float *>(dst0 + (size_t)(b + u) * 32) = x0[u];
-                *reinterpret_cast<float *>(dst0 + P.out_pitch + (size_t)(b + u) * 32) = x1[u];
-            }
+            x0[u] = n0[u];
+            x1[u] = n1[u];
         }
     }
 }

@@ -122,3 +122,26 @@ def test_coded_bits_and_compression_factor(dct, oracle, shape):
     _, coef3 = oracle.roundtrip_rgb(rgb, want_coef=True)
     bits = sum(oracle.coded_bits(oracle.zigzag_i16(coef3[c]), 0 if c == 0 else 1) for c in range(3))
     assert abs(dct.compression_factor(zz3) - 24.0 * H * W / bits) < 1e-12
+
+
+def test_coded_bits_on_a_padded_stream_and_accumulation(dct, oracle):
+    """The coded-size kernel walks the stream with its block-row pitch (DC prediction crosses the
+    padding correctly) and ADDS into the caller's counter."""
+    H, W = 40, 136
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (H, W)).astype(np.uint8)
+    _, coef = oracle.roundtrip(img, want_coef=True)
+    want = oracle.coded_bits(oracle.zigzag_i16(coef), 0)
+    buf = torch.full((H // 8, W // 8 + 5, 64), 12345, dtype=torch.int16, device="cuda")
+    view = buf[:, : W // 8, :]
+    dct.roundtrip(torch.from_numpy(img).cuda(), coef=view, zigzag=True)
+    assert dct.coded_bits(view, 0) == want
+    acc = torch.full((1,), 1000, dtype=torch.int64, device="cuda")
+    L = dct.lib()
+    for _ in range(2):
+        assert L.b200dct_zigzag_coded_bits(view.data_ptr(), view.stride(0) * 2, H, W, 0, acc.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    assert int(acc.item()) == 1000 + 2 * want
+    # argument errors
+    assert L.b200dct_zigzag_coded_bits(view.data_ptr(), 64, H, W, 0, acc.data_ptr(), None) != 0      # pitch too small
+    assert L.b200dct_zigzag_coded_bits(view.data_ptr(), view.stride(0) * 2, H, W, 2, acc.data_ptr(), None) != 0  # no such table
