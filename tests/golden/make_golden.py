@@ -48,6 +48,15 @@ def main():
     out, coef = o.roundtrip(crop, T=T, want_coef=True)
     np.savez_compressed(os.path.join(HERE, "oracle_dense_dct2.npz"), img=crop.astype(np.uint8), T=T,
                         coef=coef.astype(np.int16), out=out)
+    # 5) colour path and coded size (round 2): 48x64 RGB
+    rng = np.random.default_rng(2026)
+    yy, xx = np.mgrid[0:48, 0:64]
+    rgb = np.stack([(128 + 100 * np.sin(xx / 7.0 + c) * np.cos(yy / 9.0 - c) + rng.normal(0, 6, (48, 64))) for c in range(3)], -1)
+    rgb = rgb.clip(0, 255).astype(np.uint8)
+    out, planes, coef3 = o.roundtrip_rgb(rgb, want_planes=True, want_coef=True)
+    bits = np.array([o.coded_bits(o.zigzag_i16(coef3[c]), 0 if c == 0 else 1) for c in range(3)], np.int64)
+    np.savez_compressed(os.path.join(HERE, "oracle_rgb.npz"), rgb=rgb, out=out, planes=planes,
+                        coef=coef3.astype(np.int16), coded_bits=bits)
     print("wrote fixtures to", HERE)
 
 

@@ -171,3 +171,13 @@ def test_rgb_round_trip_structure(oracle):
     grey = np.repeat(rng.integers(0, 256, (16, 16, 1), dtype=np.uint8), 3, 2)
     _, _, cg = oracle.roundtrip_rgb(grey, want_planes=True, want_coef=True)
     assert np.count_nonzero(cg[1]) == 0 and np.count_nonzero(cg[2]) == 0
+
+
+def test_rgb_golden_fixture(oracle):
+    """tests/golden/oracle_rgb.npz (make_golden.py): the colour path and the coded sizes stay what they were."""
+    g = np.load(os.path.join(os.path.dirname(GOLD), "oracle_rgb.npz"))
+    out, planes, coef = oracle.roundtrip_rgb(g["rgb"], want_planes=True, want_coef=True)
+    assert np.array_equal(out, g["out"]) and np.array_equal(planes, g["planes"])
+    assert np.array_equal(coef.astype(np.int16), g["coef"])
+    bits = [oracle.coded_bits(oracle.zigzag_i16(coef[c]), 0 if c == 0 else 1) for c in range(3)]
+    assert bits == g["coded_bits"].tolist()
