@@ -544,6 +544,31 @@ def extras_single_gpu(m, dev, peak):
                             ("sparse_16384", m.Plan(), "HpApprDCT on the same image: identical I/O, strictly less math (lower bound for any dense kernel)")):
         ms = time_config(m, rotating(m, plan, a, b, stream), k=10)
         ex[key] = entry(ms, N2 * N2, 8, what=what, kernel_path=m.api.last_path())
+    del a, b
+    torch.cuda.empty_cache()
+    # batches of SEPARATELY ALLOCATED images in one launch per 64 images (b200dct_roundtrip_batch) against
+    # the loop of single-image calls a caller of the reference writes; the 64 x 8192^2 u8 batch is the
+    # alternative form of BASELINE configs[4] on one GPU
+    plan = m.Plan()
+    for key, n, side, dt, bpp, k in (("batch64_f32_1024", 64, 1024, torch.float32, 8, 20), ("batch64_u8_2048", 64, 2048, torch.uint8, 2, 20),
+                                     ("batch64_u8_8192", 64, 8192, torch.uint8, 2, 5)):
+        imgs = [torch.randint(0, 256, (side, side), device=dev, dtype=torch.int32).to(dt) for _ in range(n)]
+        batch = m.ImageBatch(imgs)
+
+        def bstep(i):
+            batch.run(plan=plan, stream=stream)
+
+        def lstep(i):
+            for x, y in zip(batch.imgs, batch.outs):
+                m.roundtrip(x, out=y, plan=plan, stream=stream)
+        ms = time_config(m, bstep, k=k)
+        launches = m.api.last_launch_count()
+        ex[key] = entry(ms, n * side * side, bpp, launches=launches, kernel_path=m.api.last_path(),
+                        loop_of_single_calls_ms=time_config(m, lstep, k=max(2, k // 4), warm=1),
+                        what=f"{n} separately allocated {side}^2 {'f32' if dt == torch.float32 else 'u8'} images, one batch call "
+                             f"({launches} launch) vs a Python loop of {n} b200dct_roundtrip calls")
+        del imgs, batch
+        torch.cuda.empty_cache()
     return ex
 
 
@@ -584,6 +609,31 @@ def extras_multi_gpu(m, dev, rank, world):
                               "what": f"one {H}x{Wd} u8 image striped over {world} GPUs, fused round trip, no collective; slowest rank",
                               "parity_all_ranks": m.dist.sum_over_ranks(0.0 if ok else 1.0, dev) == 0.0,
                               "parity_criterion": "coefficients bit-exact by construction; u8 pixels within 1 LSB of the oracle (2 bands per rank)"}}
+    # the alternative form of configs[4]: a batch of 64 separately allocated 8192^2 u8 images, image b on
+    # rank b mod world, every rank ONE batch call; strong scaling, no collective
+    nb, side = 64, 8192
+    mine = list(range(rank, nb, world))
+    gb = torch.Generator(device=dev).manual_seed(2000 + rank)
+    batch = m.ImageBatch([torch.randint(0, 256, (side, side), device=dev, generator=gb, dtype=torch.uint8) for _ in mine])
+
+    def bstep(i):
+        batch.run(plan=plan, stream=stream)
+
+    bstep(0)
+    m.dist.barrier()
+    torch.cuda.synchronize()
+    bms = statistics.median(timed_windows(bstep, 5, 3, stream, warm=2)) / 5
+    m.dist.barrier()
+    bms = m.dist.max_over_ranks(bms, dev)
+    bok = all(int(np.abs(batch.outs[j][a:a + 16].cpu().numpy().astype(np.int16)
+                         - o.roundtrip(batch.imgs[j][a:a + 16].cpu().numpy()).astype(np.int16)).max()) <= 1
+              for j in (0, len(mine) - 1) for a in (0, side - 16))
+    ex["u8_batch64_8192_strong"] = {"ms": bms, "gpixel_s": nb * side * side / (bms * 1e-3) / 1e9, "images_per_gpu": len(mine),
+                                    "launches_per_gpu": m.api.last_launch_count(),
+                                    "what": f"{nb} separately allocated {side}^2 u8 images, image b on rank b mod {world}, one b200dct_roundtrip_batch call per rank; slowest rank",
+                                    "parity_all_ranks": m.dist.sum_over_ranks(0.0 if bok else 1.0, dev) == 0.0}
+    del batch
+    torch.cuda.empty_cache()
     try:
         peer = m.dist.PeerImage(H, Wd, torch.uint8, dev)
         dst = peer.stripe_on(0, r0, r1)               # rows [r0, r1) of rank 0's full image

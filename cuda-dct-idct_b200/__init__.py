@@ -23,6 +23,8 @@ from .api import (  # noqa: F401
     metrics,
     roundtrip,
     roundtrip_any,
+    roundtrip_batch,
+    ImageBatch,
     roundtrip_host,
     roundtrip_rgb,
     coded_bits,
@@ -37,5 +39,5 @@ from .stripes import stripe_rows  # noqa: F401
 __all__ = [
     "ALL_COEFFS", "B200DCTError", "HostPipeline", "Plan", "build", "dct_all_blocks", "dct_all_blocks_cuda", "forward",
     "idct_all_blocks", "idct_all_blocks_cuda", "inverse", "lib", "lib_path", "metrics", "roundtrip",
-    "roundtrip_any", "roundtrip_host", "roundtrip_rgb", "coded_bits", "compression_factor", "roundtrip_with_metrics", "stripe_rows", "zigzag_mask",
+    "roundtrip_any", "roundtrip_batch", "ImageBatch", "roundtrip_host", "roundtrip_rgb", "coded_bits", "compression_factor", "roundtrip_with_metrics", "stripe_rows", "zigzag_mask",
 ]

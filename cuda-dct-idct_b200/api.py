@@ -68,6 +68,7 @@ def lib() -> C.CDLL:
         L.b200dct_metrics_workspace_bytes.restype = sz
         L.b200dct_roundtrip_metrics.argtypes = [vp, vp, i, sz, vp, i, sz, vp, i, sz, i, i, vp, vp, sz, vp]
         L.b200dct_roundtrip_any.argtypes = [vp, vp, i, sz, vp, sz, i, i, vp]
+        L.b200dct_roundtrip_batch.argtypes = [vp, i, C.POINTER(vp), C.POINTER(vp), i, sz, sz, i, i, vp]
         L.b200dct_roundtrip_host.argtypes = [vp, vp, i, vp, i, i, i]
         L.b200dct_plan_set_chroma_quant.argtypes = [vp, C.POINTER(C.c_float)]
         L.b200dct_plan_get_chroma_quant.argtypes = [vp, C.POINTER(C.c_float)]
@@ -378,6 +379,64 @@ def roundtrip_any(img, out=None, plan: Plan | None = None, stream=None):
                                            out.data_ptr(), out.stride(0) * out.element_size(), img.shape[0], img.shape[1],
                                            _stream(stream)))
     return out
+
+
+class ImageBatch:
+    """A list of separately allocated CUDA images of ONE shape, dtype (float32 or uint8) and row pitch
+    with their outputs, validated once: `run()` is then a single call of b200dct_roundtrip_batch (one
+    launch per 64 images).  `outs`: matching list (entries may be the inputs themselves), allocated
+    when omitted.  The batch keeps its tensors alive."""
+
+    def __init__(self, imgs, outs=None):
+        import torch
+
+        self.imgs = list(imgs)
+        if not self.imgs:
+            raise B200DCTError("an image batch needs at least one image")
+        first = self.imgs[0]
+        _, self._dt, self._ipitch, self.H, self.W = _plane(first)
+        with torch.cuda.device(first.device):
+            self.outs = [torch.empty_like(t) for t in self.imgs] if outs is None else list(outs)
+        if len(self.outs) != len(self.imgs):
+            raise B200DCTError("outs must have one entry per image")
+        n = len(self.imgs)
+        self._in, self._out = (C.c_void_p * n)(), (C.c_void_p * n)()
+        self._opitch = None
+        for k, (a, b) in enumerate(zip(self.imgs, self.outs)):
+            if a.dim() != 2 or b.dim() != 2 or a.device != first.device or b.device != first.device:
+                raise B200DCTError("a batch is a list of 2-d images on one device")
+            p, d, pitch, h, w = _plane(a)
+            if (d, pitch, h, w) != (self._dt, self._ipitch, self.H, self.W):
+                raise B200DCTError(f"image {k}: every image of a batch has the shape, dtype and pitch of the first")
+            q, _, qpitch = _same_plane(b, self.H, self.W, f"outs[{k}]", (a.dtype,))
+            if self._opitch is None:
+                self._opitch = qpitch
+            if qpitch != self._opitch:
+                raise B200DCTError(f"outs[{k}]: every output of a batch has the pitch of the first")
+            self._in[k], self._out[k] = p, q
+
+    def __len__(self):
+        return len(self.imgs)
+
+    def run(self, plan: Plan | None = None, stream=None):
+        with _on(self.imgs[0], stream):
+            _check(lib().b200dct_roundtrip_batch(_plan(plan)._h, len(self.imgs), self._in, self._out, self._dt,
+                                                 self._ipitch, self._opitch, self.H, self.W, _stream(stream)))
+        return self.outs
+
+
+def roundtrip_batch(imgs, outs=None, plan: Plan | None = None, stream=None):
+    """Fused round trip of a list of separately allocated CUDA images of one shape, dtype and pitch in one
+    launch per 64 images: the results are those of `roundtrip` on every image, bit for bit.  For a batch
+    that is processed repeatedly build an `ImageBatch` once and call its `run()`."""
+    imgs = list(imgs)
+    if not imgs:
+        return []
+    import torch
+
+    with _on(imgs[0], stream):      # allocation of missing outputs on the caller's stream
+        batch = ImageBatch(imgs, [torch.empty_like(t) for t in imgs] if outs is None else outs)
+    return batch.run(plan, stream)
 
 
 def roundtrip_rgb(rgb, out=None, streams=None, plan: Plan | None = None, stream=None):

@@ -806,6 +806,67 @@ extern "C" int b200dct_roundtrip(const b200dct_plan *plan, const void *img, b200
                Plane{coef_or_null, (int)coef_dt, coef_pitch}, nullptr, H, W, (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------ batches of separately allocated images
+// One launch per DIRECT_BATCH_MAX images (the third grid dimension walks the images, their plane
+// pointers travel in the kernel parameters: no device-side table, no copy, legal under stream
+// capture); consecutive launches of a longer batch overlap through programmatic dependent launch.
+// The direct family: hardware-scheduled CTAs need no per-image tensor maps, and it is the family
+// the small images a batch is made of run on anyway.
+extern "C" int b200dct_roundtrip_batch(const b200dct_plan *plan, int n_images, const void *const *imgs, void *const *outs,
+                                       b200dct_dtype dt, size_t in_pitch, size_t out_pitch, int H, int W, void *stream)
+{
+    tl_launches = 0;
+    if (!plan || n_images < 0 || (n_images > 0 && (!imgs || !outs))) return B200DCT_ERR_ARG;
+    if (dt != B200DCT_F32 && dt != B200DCT_U8) return B200DCT_ERR_ARG;
+    if (H <= 0 || W <= 0 || (H % 8) || (W % 8)) return B200DCT_ERR_SHAPE;
+    for (int i = 0; i < n_images; i++) {
+        int rc;
+        if ((rc = check_plane(Plane{imgs[i], (int)dt, in_pitch}, W, true)) != 0) return rc;
+        if ((rc = check_plane(Plane{outs[i], (int)dt, out_pitch}, W, true)) != 0) return rc;
+    }
+    if (n_images == 0) return B200DCT_OK;
+    const DevInfo di = dev_info();
+    if (!di.ok) return B200DCT_ERR_NODEVICE;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int qmode = qmode_of(plan);
+    const int qm = (!plan->sparse && qmode == Q_IMM) ? Q_PARAM : qmode;
+    int kmask = 0;
+    if (plan->sparse && plan->q_default && plan->q_fastdiv && compiled_masks())
+        for (int k = 6; k <= 10; k++)
+            if (plan->mask == b200dct_zigzag_mask(k)) kmask = k;
+    const bool finv = !kmask && use_factored_inverse(plan, MODE_RT, (int)dt);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+    DirectParams P;
+    memset(&P, 0, sizeof(P));
+    P.in_pitch = in_pitch; P.out_pitch = out_pitch;
+    P.bx = W / 8; P.by = H / 8;
+    P.coef_dt = DT_F32;
+    P.cp = plan->cp;
+    dim3 block(32, 4);
+    dim3 grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32), 1);
+    if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
+    forget_stream(s);
+    int launches = 0;
+    for (int first = 0; first < n_images; first += DIRECT_BATCH_MAX) {
+        const int n = n_images - first < DIRECT_BATCH_MAX ? n_images - first : DIRECT_BATCH_MAX;
+        P.nimg = n;
+        for (int i = 0; i < n; i++) {
+            P.img_in[i] = imgs[first + i];
+            P.img_out[i] = outs[first + i];
+        }
+        P.in = P.img_in[0]; P.out = P.img_out[0];
+        grid.z = (unsigned)n;
+        const cudaError_t e = kmask ? launch_direct_kmask(kmask, (int)dt, P, grid, block, s, pdl_for(capturing))
+                                    : launch_direct(plan->tk, MODE_RT, qm, (int)dt, finv, P, grid, block, s, pdl_for(capturing));
+        if (e != cudaSuccess) return (int)e;
+        launches++;
+    }
+    tl_launches = launches;
+    tl_path = "direct";
+    return B200DCT_OK;
+}
+
 // ------------------------------------------------------------------ any size / any alignment
 extern "C" int b200dct_roundtrip_any(const b200dct_plan *plan, const void *img, b200dct_dtype dt, size_t in_pitch,
                                      void *out, size_t out_pitch, int H, int W, void *stream)

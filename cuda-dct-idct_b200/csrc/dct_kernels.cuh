@@ -91,6 +91,7 @@ __device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams 
 }
 
 // ============================================================== direct family
+constexpr int DIRECT_BATCH_MAX = 64; // images per launch of the batch entry point (1 KiB of kernel parameters)
 struct DirectParams {
     const void *in;   // FWD/RT: pixels (PIX dtype); INV: coefficients (coef_dt)
     void *out;        // FWD: coefficients (coef_dt); INV/RT: pixels (PIX dtype)
@@ -101,6 +102,12 @@ struct DirectParams {
     int coef_dt;      // DT_F32 / DT_I16
     double *partials; // METRICS kernels: 3 doubles per CTA {sum (x-y)^2, sum x^2, non-zero coefficients}
     int zz_smem;      // 1: the launch carries ZZ_SMEM_BYTES of dynamic shared memory for the zig-zag stream transpose
+    // batch of separately allocated images of one shape (b200dct_roundtrip_batch): image z of the launch
+    // is blockIdx.z, its planes come from these tables instead of in / out (pixels only: no coefficient
+    // plane, no side effect, no metrics); 0 = the single image above
+    int nimg;
+    const void *img_in[DIRECT_BATCH_MAX];
+    void *img_out[DIRECT_BATCH_MAX];
     CommonParams cp;
 };
 constexpr int ZZ_SMEM_BYTES = 4 * 4096; // one 4 KiB span per warp of the 128-thread CTA
@@ -252,12 +259,15 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
 
     float2 p[8][4];
     // ---- load
+    // batch launches: the planes of image blockIdx.z (a register-indexed read of the parameter bank,
+    // warp-uniform); the output pointer is fetched again at the store so that it is not live in between
+    const void *const in_plane = P.nimg ? P.img_in[blockIdx.z] : P.in;
     if constexpr (MODE == MODE_INV) {
-        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch;
+        const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch;
         if (P.coef_dt == DT_F32) {
             sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
         } else if (P.coef_dt == DT_I16ZZ) { // pitch = bytes per block-row of the stream
-            const char *row = (const char *)P.in + (size_t)by * P.in_pitch;
+            const char *row = (const char *)in_plane + (size_t)by * P.in_pitch;
             if (zz_coop) ld_warp_zigzag(row + (size_t)blockIdx.y * 4096, zz_buf, threadIdx.x, p);
             else ld_block_zigzag(row + (size_t)bxi * 128, p);
         } else {
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
             });
         }
     } else if constexpr (PIX == DT_F32) {
-        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
+        const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
         sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch, p[IC(r)]); });
         sfor<8>([&](auto r) { shift_row(p[IC(r)], -128.0f); }); // sub_matrix_scalar, utils_kernels.cu:16
         if constexpr (MODE == MODE_FWD) {
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
             }
         }
     } else {
-        const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
+        const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
         sfor<8>([&](auto r) {
             unpack_u8_shifted(__ldg(reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch)), p[IC(r)]);
         });
@@ -310,10 +320,11 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     });
 
     // ---- store
+    void *const out_plane = P.nimg ? P.img_out[blockIdx.z] : P.out;
     if constexpr (MODE == MODE_FWD) {
-        store_coef(P.out, P.out_pitch, p);
+        store_coef(out_plane, P.out_pitch, p);
     } else if constexpr (PIX == DT_F32) {
-        char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 32;
+        char *dst = (char *)out_plane + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 32;
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
         sfor<8>([&](auto r) {
             if constexpr (!BIASED) shift_row(p[IC(r)], 128.0f); // add_matrix_scalar, utils_kernels.cu:29
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
             }
         });
     } else {
-        char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 8;
+        char *dst = (char *)out_plane + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 8;
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
         sfor<8>([&](auto r) {
             const uint2 w = BIASED ? pack_u8_row(p[IC(r)]) : pack_u8_plus128(p[IC(r)]);

@@ -184,6 +184,21 @@ int b200dct_roundtrip(const b200dct_plan *plan,
                       void *coef_or_null, b200dct_dtype coef_dt, size_t coef_pitch,
                       int H, int W, void *stream);
 
+/* Fused round trip of a BATCH of n separately allocated images of one shape and dtype (F32 or U8),
+ * e.g. the 64 8192^2 images of BASELINE configs[4] or a queue of the README's 256^2..2048^2 images:
+ * what a caller of the reference does with a loop of dct_all_blocks_cuda / idct_all_blocks_cuda
+ * pairs over its images (main_newAppr.cu:99,120 / benchmark_fastAppr.cu:79,91 process one image per
+ * program run; README.md:46 averages 100 such runs), in ONE launch per B200DCT_BATCH_MAX images
+ * instead of 6 per image.
+ * imgs / outs: HOST arrays of n device pointers (read before the call returns); every image obeys
+ * the rules of b200dct_roundtrip (pitches shared by all images); outs[i] may equal imgs[i].
+ * Results are those of n b200dct_roundtrip calls, bit for bit.  Legal under stream capture. */
+#define B200DCT_BATCH_MAX 64
+int b200dct_roundtrip_batch(const b200dct_plan *plan, int n_images,
+                            const void *const *imgs, void *const *outs,
+                            b200dct_dtype dt, size_t in_pitch, size_t out_pitch,
+                            int H, int W, void *stream);
+
 /* Round trip for ANY image: H and W need not be multiples of 8 and nothing needs to be aligned
  * beyond the element size (SURVEY.md section 8f "generality"; the reference silently computes
  * garbage there, main_newAppr.cu:261-262).  Aligned multiples of 8 go straight to
