@@ -573,6 +573,15 @@ static bool compiled_masks() // env B200DCT_COMPILED_MASKS=0: retained-coefficie
     return v;
 }
 
+// AUTO's family choice for a call that moves bytes_per_px (explained where run() makes it)
+constexpr unsigned long long TMA_BIG_PIXELS = 28ull << 20, TMA_HUGE_PIXELS = 64ull << 20;
+static bool prefers_tma(const b200dct_plan *pl, size_t bytes_per_px, int H, int W)
+{
+    const unsigned long long px = (unsigned long long)H * (unsigned long long)W;
+    return pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && px >= TMA_BIG_PIXELS) ||
+           (bytes_per_px >= 4 && pl->tk == TK_DENSE_SYM && px >= TMA_HUGE_PIXELS);
+}
+
 static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef, float *shifted, int H, int W,
                cudaStream_t stream, double *partials = nullptr, double *acc = nullptr)
 {
@@ -603,15 +612,14 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     // one CTA per SM) lose to the direct family (C-loop timings with dependent launch,
     // profiles/r01_small_sizes.txt): 256^2 3.4 vs 6.7 us, 2048^2 7.9 vs 9.7, 4096^2 22.9 vs 24.6,
     // 5120^2 34.9 vs 35.0, 6144^2 48.9 vs 48.0, 8192^2 83.8 vs 81.8.
-    const bool big = (unsigned long long)H * (unsigned long long)W >= (28ull << 20);
+    // (TMA_BIG_PIXELS = 28 Mpixel)
     // Symmetric dense T (16+16 FMA/px).  Before early tile loads the direct family won up to 12288^2
     // (84.6 vs 88.0 us at 8192^2, 187.7 vs 189.0 at 12288^2) and the persistent TMA kernel beyond
     // (16384^2: 321.9 vs 333.9 us); with early loads across launch boundaries the TMA family wins from
     // 8192^2 on: 80.2 vs 84.7 us, 16384^2 314.7 vs 330.9 us (profiles/r02_dense_paths.txt).  Ordered-chain
     // dense kernels stay on the direct family.
-    const bool huge = (unsigned long long)H * (unsigned long long)W >= (64ull << 20);
-    const bool prefer_tma = pl->path == B200DCT_PATH_TMA || (bytes_per_px >= 4 && pl->sparse && big) ||
-                            (bytes_per_px >= 4 && pl->tk == TK_DENSE_SYM && huge);
+    // (TMA_HUGE_PIXELS = 64 Mpixel)
+    const bool prefer_tma = prefers_tma(pl, bytes_per_px, H, W);
     // Under stream capture the launch takes a ticket-counter pair of its own (see SchedRing); when
     // none is left (or the pools do not exist yet) AUTO falls back to the hardware-scheduled
     // direct family (86.9 us at 8192^2), which beats the TMA family's static split (99.8 us).
@@ -828,6 +836,23 @@ extern "C" int b200dct_roundtrip_batch(const b200dct_plan *plan, int n_images, c
     const DevInfo di = dev_info();
     if (!di.ok) return B200DCT_ERR_NODEVICE;
     cudaStream_t s = (cudaStream_t)stream;
+    // Images large enough for the persistent TMA kernels to win (f32 from 28 Mpixel, see run()) go through
+    // the single-image path one by one: consecutive launches overlap (dependent launch, early tile loads),
+    // 79.5 against 86 us per 8192^2 f32 image on the direct family.
+    if (plan->path != B200DCT_PATH_DIRECT && prefers_tma(plan, 2 * elem_size((int)dt), H, W)) {
+        int launches = 0;
+        const char *path = "none";
+        for (int i = 0; i < n_images; i++) {
+            const int rc = run(plan, MODE_RT, Plane{imgs[i], (int)dt, in_pitch}, Plane{outs[i], (int)dt, out_pitch},
+                               Plane{nullptr, DT_F32, 0}, nullptr, H, W, s);
+            if (rc != B200DCT_OK) return rc;
+            launches += tl_launches;
+            path = tl_path;
+        }
+        tl_launches = launches;
+        tl_path = path;
+        return B200DCT_OK;
+    }
     const int qmode = qmode_of(plan);
     const int qm = (!plan->sparse && qmode == Q_IMM) ? Q_PARAM : qmode;
     int kmask = 0;

@@ -192,7 +192,9 @@ int b200dct_roundtrip(const b200dct_plan *plan,
  * instead of 6 per image.
  * imgs / outs: HOST arrays of n device pointers (read before the call returns); every image obeys
  * the rules of b200dct_roundtrip (pitches shared by all images); outs[i] may equal imgs[i].
- * Results are those of n b200dct_roundtrip calls, bit for bit.  Legal under stream capture. */
+ * Results are those of n b200dct_roundtrip calls, bit for bit.  Legal under stream capture.
+ * (Images large enough for the persistent TMA kernels -- F32 from 28 Mpixel -- are launched one by
+ * one on that family instead, which is faster there; b200dct_last_launch_count() tells.) */
 #define B200DCT_BATCH_MAX 64
 int b200dct_roundtrip_batch(const b200dct_plan *plan, int n_images,
                             const void *const *imgs, void *const *outs,

@@ -127,9 +127,11 @@ def test_batch_of_full_size_images_matches_single_calls(dct):
     """Four separately allocated 4096^2 f32 images and four 8192^2 u8 images: the batch launch against
     the single-image entry point (whatever family AUTO picks for it), whole images, bit for bit."""
     g = torch.Generator(device="cuda").manual_seed(5)
-    for N, dt in ((4096, torch.float32), (8192, torch.uint8)):
+    # 8192^2 f32 images are large enough for the persistent TMA kernels: launched one by one on that family
+    for N, dt, path, launches in ((4096, torch.float32, "direct", 1), (8192, torch.uint8, "direct", 1), (8192, torch.float32, "tma", 4)):
         imgs = [torch.randint(0, 256, (N, N), device="cuda", generator=g, dtype=torch.int32).to(dt) for _ in range(4)]
         outs = dct.roundtrip_batch(imgs)
+        assert (dct.api.last_path(), dct.api.last_launch_count()) == (path, launches)
         for a, b in zip(imgs, outs):
             ref = dct.roundtrip(a)
             assert torch.equal(ref.view(torch.int32) if dt == torch.float32 else ref, b.view(torch.int32) if dt == torch.float32 else b)
