@@ -20,22 +20,24 @@
 namespace b200dct {
 // one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
 #define B200_DECL(tag)                                                                                                  \
-    cudaError_t launch_direct_##tag(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);     \
+    cudaError_t launch_direct_##tag(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm); \
     cudaError_t launch_direct_metrics_##tag(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);      \
     cudaError_t launch_tma_##tag(int mode, int pix, bool finv, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);
 B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2) B200_DECL(y1) B200_DECL(y2)
 #undef B200_DECL
-cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_direct_k.cu
+cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm = nullptr); // inst_direct_k.cu
 cudaError_t launch_any_f32(int tk, int qm, bool finv, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl); // inst_any_f32.cu
 cudaError_t launch_any_u8(int tk, int qm, bool finv, const AnyParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);  // inst_any_u8.cu
 cudaError_t launch_mma(bool fastdiv, const MmaParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl);                           // inst_mma.cu
 cudaError_t launch_tma_kmask(int k, int pix, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);          // inst_tma_k.cu
 
-static cudaError_t launch_direct(int tk, int mode, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl)
+// ctas_per_sm != NULL: no launch, only the resident-CTA count of the kernel the arguments select
+static cudaError_t launch_direct(int tk, int mode, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl, int *ctas_per_sm = nullptr)
 {
-    if (tk == TK_DENSE_SYM) return q == 1 ? launch_direct_y1(mode, pix, finv, P, g, b, s, pdl) : launch_direct_y2(mode, pix, finv, P, g, b, s, pdl);
-    if (tk == TK_HAWEEL) return q == 0 ? launch_direct_s0(mode, pix, finv, P, g, b, s, pdl) : q == 1 ? launch_direct_s1(mode, pix, finv, P, g, b, s, pdl) : launch_direct_s2(mode, pix, finv, P, g, b, s, pdl);
-    return q == 1 ? launch_direct_d1(mode, pix, finv, P, g, b, s, pdl) : launch_direct_d2(mode, pix, finv, P, g, b, s, pdl);
+    int *c = ctas_per_sm;
+    if (tk == TK_DENSE_SYM) return q == 1 ? launch_direct_y1(mode, pix, finv, P, g, b, s, pdl, c) : launch_direct_y2(mode, pix, finv, P, g, b, s, pdl, c);
+    if (tk == TK_HAWEEL) return q == 0 ? launch_direct_s0(mode, pix, finv, P, g, b, s, pdl, c) : q == 1 ? launch_direct_s1(mode, pix, finv, P, g, b, s, pdl, c) : launch_direct_s2(mode, pix, finv, P, g, b, s, pdl, c);
+    return q == 1 ? launch_direct_d1(mode, pix, finv, P, g, b, s, pdl, c) : launch_direct_d2(mode, pix, finv, P, g, b, s, pdl, c);
 }
 static cudaError_t launch_direct_metrics(int tk, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
 {
@@ -473,11 +475,15 @@ struct Range {
 struct LastLaunch {
     int dev = -1;
     cudaStream_t stream = nullptr;
-    bool tma = false;
-    Range w[2];
+    bool tma = false;     // persistent TMA-family launch that fills the machine (see above)
+    bool direct = false;  // direct-family launch with more CTAs than the machine holds at once (see below)
+    Range w[3];
+    bool chain_ok = true; // false once the record has been taken over by another stream (its counter may still be fed)
+    unsigned long long expected = 0; // value of the record's completion counter once every recorded launch has completed
 };
 constexpr int LAST_SLOTS = 16;
 LastLaunch g_last[LAST_SLOTS];
+unsigned long long *g_chain[64] = {}; // per device: one completion counter per record
 std::mutex g_last_mu;
 Range plane_range(const void *p, size_t pitch, size_t row_bytes, int H)
 {
@@ -497,34 +503,92 @@ bool early_loads_enabled()
     }();
     return v;
 }
-// Returns whether a TMA launch reading `rd` on `stream` may load early, and records this launch.
-// The caller holds g_last_mu and keeps it until the kernel has been enqueued: the record order must be
-// the stream order even when several host threads launch on one stream.
-bool record_launch_locked(cudaStream_t stream, bool tma, const Range &rd, const Range &w0, const Range &w1)
+// The direct family (hardware-scheduled 128-thread CTAs, several per SM) has its own version of the argument:
+// a dependent launch starts once every CTA of its predecessor has STARTED (executed launch_dependents).
+// If the predecessor has more CTAs than the machine can hold at once (grid > resident CTAs per SM x SMs,
+// the occupancy of that very kernel), "all started" implies "some exited", and a CTA only exits after its
+// griddepcontrol.wait -- so again everything older than the predecessor is complete when a successor CTA
+// runs, and only the predecessor's own writes matter.  A direct-family round trip whose input is disjoint
+// from them loads AND transforms its blocks before its wait (L2-coherent loads) and only holds back its
+// stores: its CTAs work in the slots the predecessor's last wave leaves idle instead of sitting at the wait
+// (8192^2 u8: 11 waves of ~5 us, on average half a wave idle per launch boundary).
+//
+// Both arguments are about the library's own kernels; what the CALLER enqueues between two calls is
+// invisible to the host side.  A kernel of the caller that writes the next call's input is covered on
+// the device: every machine-filling launch feeds a per-(device, stream) completion counter (direct
+// family: one increment per CTA at its end; TMA family: one by the last warp out), the host knows the
+// value the counter has once the predecessor is complete, and a successor only takes the early path
+// when it READS a smaller value -- the predecessor is then provably still running, so nothing enqueued
+// after it (which, launched the ordinary way, starts only when the predecessor has completed) can stand
+// between the two; otherwise the successor waits first like any dependent launch.  (Not covered: foreign
+// kernels themselves launched with programmatic stream serialization between two calls of the library.)
+struct LaunchTicket {
+    LastLaunch *rec = nullptr;
+    bool early = false;                  // this launch may take the early path (subject to the device-side check)
+    unsigned long long *chain = nullptr; // the record's completion counter (NULL: none, no early path around this launch)
+    unsigned long long target = 0;       // its value once the predecessor is complete
+};
+// Step 1, before the launch: may a launch of family `tma` / direct reading `rd` on `stream` load early?
+// (fills: it satisfies its family's machine-filling condition.)  Leaves the record cleared; commit_launch_locked
+// fills it in once the kernel is in the stream.  The caller holds g_last_mu across both steps and the launch:
+// the record order must be the stream order even when several host threads launch on one stream.
+LaunchTicket begin_launch_locked(cudaStream_t stream, bool tma, bool fills, bool may_allocate, const Range &rd)
 {
+    LaunchTicket t;
     int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return t;
     LastLaunch *e = nullptr, *freeslot = nullptr;
     for (auto &x : g_last) {
         if (x.dev == dev && x.stream == stream) e = &x;
         if (x.dev < 0 && !freeslot) freeslot = &x;
     }
-    bool early = false;
-    if (e) early = tma && e->tma && disjoint(rd, e->w[0]) && disjoint(rd, e->w[1]);
-    if (!e) e = freeslot ? freeslot : &g_last[((uintptr_t)stream >> 4) % LAST_SLOTS]; // evicting a record is always safe (no early loads)
-    e->dev = dev;
-    e->stream = stream;
-    e->tma = tma;
-    e->w[0] = w0;
-    e->w[1] = w1;
-    return early && early_loads_enabled();
+    const bool known = e != nullptr;
+    if (!e) {
+        if (freeslot) e = freeslot;
+        else { // evicting a record is always safe: no early path on it any more
+            e = &g_last[((uintptr_t)stream >> 4) % LAST_SLOTS];
+            e->chain_ok = false;
+        }
+        e->expected = 0; // a fresh record's counter has never been fed; an evicted one has no counter any more
+        e->dev = dev;
+        e->stream = stream;
+        e->tma = e->direct = false;
+    }
+    if (e->chain_ok && !g_chain[dev] && may_allocate) {
+        unsigned long long *p = nullptr;
+        if (cudaMalloc(&p, LAST_SLOTS * sizeof(unsigned long long)) == cudaSuccess) {
+            if (cudaMemset(p, 0, LAST_SLOTS * sizeof(unsigned long long)) == cudaSuccess) g_chain[dev] = p;
+            else cudaFree(p);
+        }
+    }
+    t.rec = e;
+    t.chain = (e->chain_ok && g_chain[dev]) ? g_chain[dev] + (e - g_last) : nullptr;
+    t.target = e->expected;
+    // (TMA family: the successor must not fit beside the predecessor either, i.e. satisfy the condition itself)
+    t.early = known && t.chain && (tma ? (fills && e->tma) : e->direct) && rd.lo != rd.hi && disjoint(rd, e->w[0]) &&
+              disjoint(rd, e->w[1]) && disjoint(rd, e->w[2]) && early_loads_enabled();
+    e->tma = e->direct = false; // until committed
+    return t;
+}
+// Step 2, after a successful launch: this launch as the next one's predecessor.  feeds: the kernel was
+// given the counter and adds `inc` to it in total.
+void commit_launch_locked(const LaunchTicket &t, bool tma, bool feeds, unsigned long long inc, const Range &w0, const Range &w1,
+                          const Range &w2 = Range{})
+{
+    if (!t.rec) return;
+    t.rec->tma = tma && feeds;
+    t.rec->direct = !tma && feeds;
+    t.rec->w[0] = w0;
+    t.rec->w[1] = w1;
+    t.rec->w[2] = w2;
+    if (feeds) t.rec->expected += inc;
 }
 } // namespace
 namespace b200dct {
 void forget_stream(cudaStream_t s)
 {
     std::lock_guard<std::mutex> lk(g_last_mu);
-    record_launch_locked(s, false, Range{}, Range{}, Range{});
+    begin_launch_locked(s, false, false, false, Range{}); // leaves the record cleared
 }
 }
 
@@ -717,16 +781,19 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         // folds it into acc -- one launch.  Static split: the first 24 bytes of the caller's workspace,
         // zeroed before and folded after the kernel.
         std::unique_lock<std::mutex> launch_order(g_last_mu); // held until this kernel is in the stream
-        {
-            const Range rd = plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H);
-            const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
-            const Range w1 = plane_range(coef.ptr, coef.pitch, (size_t)W * elem_size(coef.dt), H);
-            // the argument above needs the predecessor to occupy every SM (grid == SM count) and neither
-            // launch to fit beside the other on one SM: both take more than half of its shared memory
-            const bool heavy = smem > (size_t)(di.smem_optin / 2) + 1024;
-            const bool early = record_launch_locked(stream, !capturing && pdl_for(capturing) && grid >= di.sms && heavy, rd, w0, w1);
-            P.early_loads = (early && !capturing && pdl_for(capturing)) ? 1 : 0;
-        }
+        const Range rd = plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H);
+        const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
+        const Range w1 = plane_range(coef.ptr, coef.pitch, (size_t)W * elem_size(coef.dt), H);
+        // the argument above needs the predecessor to occupy every SM (grid == SM count) and neither
+        // launch to fit beside the other on one SM: both take more than half of its shared memory
+        const bool heavy = smem > (size_t)(di.smem_optin / 2) + 1024;
+        const bool fills = !capturing && pdl_for(capturing) && grid >= di.sms && heavy && P.sched != nullptr;
+        const LaunchTicket ticket = begin_launch_locked(stream, true, fills, !capturing, rd);
+        const bool feeds = fills && ticket.chain != nullptr;
+        P.early_loads = ticket.early ? 1 : 0;
+        P.chain = (feeds || ticket.early) ? ticket.chain : nullptr;
+        P.chain_target = ticket.target;
+        P.chain_feed = feeds ? 1 : 0;
         bool separate_finish = false;
         if (partials) {
             P.macc = sched_macc(P.sched);
@@ -742,6 +809,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         cudaError_t e = kmask
                             ? launch_tma_kmask(kmask, pix, P, grid, nw * 32, smem, stream, pdl_for(capturing))
                             : launch_tma(pl->tk, mode, qm, pix, finv, P, grid, nw * 32, smem, stream, pdl_for(capturing) && !separate_finish);
+        if (e == cudaSuccess) commit_launch_locked(ticket, true, feeds, 1, w0, w1);
         launch_order.unlock();
         if (e != cudaSuccess) return (int)e;
         tl_launches = 1;
@@ -755,7 +823,6 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         return B200DCT_OK;
     }
 
-    forget_stream(stream);
     DirectParams P;
     memset(&P, 0, sizeof(P));
     P.in = in.ptr; P.in_pitch = in.pitch;
@@ -773,6 +840,7 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     if (partials) {
         // fused metrics: per-CTA partials, then one fixed-order reduction into acc[0..2]
         if (mode != MODE_RT || in.ptr == out.ptr) return B200DCT_ERR_ARG;
+        forget_stream(stream);
         kmask = 0;
         P.partials = partials;
         e = launch_direct_metrics(pl->tk, qm, pix, finv, P, grid, block, stream);
@@ -783,8 +851,34 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         tl_path = "direct";
         return B200DCT_OK;
     }
-    if (kmask) e = launch_direct_kmask(kmask, pix, P, grid, block, stream, pdl_for(capturing));
-    else e = launch_direct(pl->tk, mode, qm, pix, finv, P, grid, block, stream, pdl_for(capturing));
+    const bool pdl = pdl_for(capturing);
+    {
+        // early loads (see record_launch_locked): this launch as a successor, and as the next one's predecessor
+        std::lock_guard<std::mutex> launch_order(g_last_mu); // held until this kernel is in the stream
+        int per_sm = 0;
+        if (pdl && !capturing) {
+            if (kmask) launch_direct_kmask(kmask, pix, P, grid, block, stream, pdl, &per_sm);
+            else launch_direct(pl->tk, mode, qm, pix, finv, P, grid, block, stream, pdl, &per_sm);
+        }
+        const unsigned long long ctas = (unsigned long long)grid.x * grid.y;
+        const bool fills = per_sm > 0 && ctas > (unsigned long long)per_sm * (unsigned long long)di.sms;
+        const bool eligible = pdl && !capturing && mode == MODE_RT && !coef.ptr;
+        const Range rd = eligible ? plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H) : Range{};
+        const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
+        const Range w1 = plane_range(coef.ptr, coef.pitch, coef_dt == DT_I16ZZ ? (size_t)(W / 8) * 128 : (size_t)W * elem_size(coef.dt),
+                                     coef_dt == DT_I16ZZ ? H / 8 : H);
+        const Range w2 = plane_range(shifted, in.pitch, (size_t)W * 4, H);
+        const LaunchTicket ticket = begin_launch_locked(stream, false, fills, !capturing, rd);
+        const bool feeds = fills && ticket.chain != nullptr;
+        const unsigned long long machine = (unsigned long long)per_sm * (unsigned long long)di.sms;
+        P.early = ticket.early ? (int)(ctas < machine ? ctas : machine) : 0; // CTAs beyond one machine-full start after the predecessor anyway
+        P.chain = (feeds || ticket.early) ? ticket.chain : nullptr;
+        P.chain_target = ticket.target;
+        P.chain_feed = feeds ? (int)(ctas < 1024 ? ctas : 1024) : 0;         // the last CTAs of the grid feed the counter
+        if (kmask) e = launch_direct_kmask(kmask, pix, P, grid, block, stream, pdl);
+        else e = launch_direct(pl->tk, mode, qm, pix, finv, P, grid, block, stream, pdl);
+        if (e == cudaSuccess) commit_launch_locked(ticket, false, feeds, (unsigned long long)P.chain_feed, w0, w1, w2);
+    }
     if (e != cudaSuccess) return (int)e;
     tl_launches = 1;
     tl_path = "direct";

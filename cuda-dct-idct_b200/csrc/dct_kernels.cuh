@@ -91,6 +91,13 @@ __device__ __forceinline__ void run_block(float2 (&p)[8][4], const CommonParams 
 }
 
 // ============================================================== direct family
+// the completion counters of the early-load protocol are read past every cache level that could be stale
+__device__ __forceinline__ unsigned long long ld_counter(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 constexpr int DIRECT_BATCH_MAX = 64; // images per launch of the batch entry point (1 KiB of kernel parameters)
 struct DirectParams {
     const void *in;   // FWD/RT: pixels (PIX dtype); INV: coefficients (coef_dt)
@@ -106,6 +113,20 @@ struct DirectParams {
     // is blockIdx.z, its planes come from these tables instead of in / out (pixels only: no coefficient
     // plane, no side effect, no metrics); 0 = the single image above
     int nimg;
+    // early (fused round trips without coefficient plane only): the host has established that nothing this
+    // launch READS is written by the launch it may overlap with (see early loads, b200dct.cu): the block is
+    // loaded (L2-coherent loads) and transformed before griddepcontrol.wait, only the stores wait for the
+    // predecessor to complete -- CTAs of this launch work in the slots the predecessor's last wave leaves idle
+    // early = E > 0: the first E CTAs of the grid (one machine-full: later CTAs only start once these have
+    // left, i.e. after the predecessor completed) may take that path.
+    int early;
+    // completion counter of the (device, stream) record (b200dct.cu): chain_feed = F > 0: the last F CTAs of
+    // the grid add 1 each at their end; a CTA takes the early path only if the counter still reads below
+    // chain_target, i.e. the predecessor is provably still running.  (One reader per CTA, F <= 1024 feeders:
+    // 32768 warps polling one L2 line per launch cost the HBM-bound kernels 2-15 us.)
+    int chain_feed;
+    unsigned long long *chain;
+    unsigned long long chain_target;
     const void *img_in[DIRECT_BATCH_MAX];
     void *img_out[DIRECT_BATCH_MAX];
     CommonParams cp;
@@ -119,6 +140,13 @@ __device__ __forceinline__ void ld_row_f32(const void *base, float2 (&r)[4])
     // rows it read (the reference's in-place sub_matrix_scalar), which rules out ld.global.nc
     const float4 a = reinterpret_cast<const float4 *>(base)[0];
     const float4 b = reinterpret_cast<const float4 *>(base)[1];
+    r[0] = make_float2(a.x, a.y); r[1] = make_float2(a.z, a.w);
+    r[2] = make_float2(b.x, b.y); r[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void ld_row_f32_cg(const void *base, float2 (&r)[4]) // L2 only: never a stale L1 line
+{
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(base));
+    const float4 b = __ldcg(reinterpret_cast<const float4 *>(base) + 1);
     r[0] = make_float2(a.x, a.y); r[1] = make_float2(a.z, a.w);
     r[2] = make_float2(b.x, b.y); r[3] = make_float2(b.z, b.w);
 }
@@ -250,7 +278,17 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     unsigned i_xx = 0, i_xy = 0, i_yy = 0; // u8 metrics
     // programmatic dependent launch (no-ops unless the host asked for it): see k_tma
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool early = false;
+    if constexpr (MODE == MODE_RT && !METRICS) {
+        if (P.early != 0 && P.coef == nullptr &&
+            (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x < (unsigned)P.early) { // CTA-uniform
+            __shared__ int s_early;
+            if (threadIdx.x == 0 && threadIdx.y == 0) s_early = ld_counter(P.chain) < P.chain_target; // thread (0,0) is always valid
+            __syncthreads();
+            early = s_early != 0;
+        }
+    }
+    if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // zig-zag stream: full warps transpose their 4 KiB span through shared memory (warp-uniform)
     extern __shared__ uint8_t zz_raw[];
@@ -277,7 +315,8 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         }
     } else if constexpr (PIX == DT_F32) {
         const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
-        sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch, p[IC(r)]); });
+        if (early) sfor<8>([&](auto r) { ld_row_f32_cg(src + IC(r) * P.in_pitch, p[IC(r)]); });
+        else sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch, p[IC(r)]); });
         sfor<8>([&](auto r) { shift_row(p[IC(r)], -128.0f); }); // sub_matrix_scalar, utils_kernels.cu:16
         if constexpr (MODE == MODE_FWD) {
             if (P.shifted) {
@@ -287,9 +326,10 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         }
     } else {
         const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 8;
-        sfor<8>([&](auto r) {
-            unpack_u8_shifted(__ldg(reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch)), p[IC(r)]);
-        });
+        uint2 w[8];
+        if (early) sfor<8>([&](auto r) { w[IC(r)] = __ldcg(reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch)); });
+        else sfor<8>([&](auto r) { w[IC(r)] = __ldg(reinterpret_cast<const uint2 *>(src + IC(r) * P.in_pitch)); });
+        sfor<8>([&](auto r) { unpack_u8_shifted(w[IC(r)], p[IC(r)]); });
     }
 
     auto store_coef = [&](void *plane, size_t pitch, float2 (&c)[8][4]) {
@@ -320,6 +360,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     });
 
     // ---- store
+    if (early) asm volatile("griddepcontrol.wait;" ::: "memory"); // every global write waits for the predecessor
     void *const out_plane = P.nimg ? P.img_out[blockIdx.z] : P.out;
     if constexpr (MODE == MODE_FWD) {
         store_coef(out_plane, P.out_pitch, p);
@@ -356,6 +397,11 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         });
     }
 
+    if constexpr (!METRICS) {
+        if (P.chain_feed && threadIdx.x == 0 && threadIdx.y == 0 &&
+            (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + (unsigned)P.chain_feed >= gridDim.x * gridDim.y * gridDim.z)
+            atomicAdd(P.chain, 1ull); // one of the last CTAs of the grid is (as good as) done
+    }
     if constexpr (METRICS) {
         if constexpr (PIX == DT_U8) {
             m_sse = (float)(i_xx + i_yy - 2u * i_xy);
@@ -374,6 +420,20 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
             P.partials[cta * 3 + lane] = (red[lane][0] + red[lane][1]) + (red[lane][2] + red[lane][3]);
         }
     }
+}
+
+// Resident CTAs per SM of one instantiation (cached): the host needs it to decide whether a launch
+// has more CTAs than the machine holds at once (early loads of its successor, b200dct.cu).
+template <void (*KERNEL)(DirectParams)>
+inline int direct_ctas_per_sm(size_t smem)
+{
+    static int cached[2] = {-1, -1};
+    int &v = cached[smem ? 1 : 0];
+    if (v < 0) {
+        int n = 0;
+        v = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, KERNEL, 128, smem) == cudaSuccess ? n : 0;
+    }
+    return v;
 }
 
 // ============================================================== TMA family
@@ -406,6 +466,11 @@ struct TmaParams {
     // overlap with (see early_loads_ok in b200dct.cu): tile loads start before griddepcontrol.wait,
     // every global write (TMA stores, metrics atomics) still waits for the predecessor to complete
     int early_loads;
+    // completion counter of the (device, stream) record: chain_feed = 1: the last warp out adds 1; early_loads = 1:
+    // a warp only loads early if the counter still reads below chain_target (predecessor provably still running)
+    int chain_feed;
+    unsigned long long *chain;
+    unsigned long long chain_target;
     uint32_t bx;          // blocks per image row (lanes of a right-edge tile beyond it hold TMA zero fill, not pixels)
     CommonParams cp;
 };
@@ -623,6 +688,10 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
     // the next kernel in the stream take this SM the moment this CTA leaves it, and do not
     // touch global memory before every earlier kernel has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // early loads: ONE thread of the CTA reads the completion counter (1184 warps polling one L2 line cost
+    // 0.5 us per launch); issued here, consumed after the barrier set-up below
+    unsigned long long chain_seen = 0;
+    if (P.early_loads && threadIdx.x == 0) chain_seen = ld_counter(P.chain);
     if (lane == 0) {
         mbar_init(bar0, 1);
         if constexpr (METRICS) mbar_init(bar0 + 8, 1);
@@ -639,14 +708,21 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
 #endif
     }
     // Only lane 0 ever touches global memory (TMA loads / stores, scheduler and metrics atomics).
-    bool dep_done = !P.early_loads;
+    bool early = false;
+    if (P.early_loads) { // CTA-uniform; the only CTA-wide barrier of the kernel, before any work exists
+        __shared__ int s_early;
+        if (threadIdx.x == 0) s_early = chain_seen < P.chain_target;
+        __syncthreads();
+        early = s_early != 0;
+    }
+    bool dep_done = !early;
     auto ensure_dep = [&]() { // lane 0, before its first global write
         if (!dep_done) {
             asm volatile("griddepcontrol.wait;" ::: "memory");
             dep_done = true;
         }
     };
-    if (!P.early_loads) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (lane == 0 && tile < P.ntiles) issue_load(tile);
     __syncwarp();
 
@@ -794,6 +870,7 @@ __global__ void B200DCT_TMA_BOUNDS k_tma(const __grid_constant__ TmaParams P)
                 }
                 sched[0] = 0;
                 sched[1] = 0;
+                if (P.chain_feed) atomicAdd(P.chain, 1ull); // this launch is (as good as) complete
                 __threadfence();
             }
         }

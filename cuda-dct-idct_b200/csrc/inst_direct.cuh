@@ -10,6 +10,10 @@ namespace b200dct {
 
 #define B200_DIRECT_CASE(M, X, F)                                                   \
     if (mode == (M) && pix == (X) && finv == (F)) {                                 \
+        if (ctas_per_sm) {                                                          \
+            *ctas_per_sm = direct_ctas_per_sm<k_direct<M, INST_SPARSE, INST_Q, X, false, F>>(P.zz_smem ? ZZ_SMEM_BYTES : 0); \
+            return cudaSuccess;                                                     \
+        }                                                                           \
         cudaLaunchConfig_t cfg = {};                                                \
         cfg.gridDim = grid;                                                         \
         cfg.blockDim = block;                                                       \
@@ -23,7 +27,8 @@ namespace b200dct {
         return cudaLaunchKernelEx(&cfg, k_direct<M, INST_SPARSE, INST_Q, X, false, F>, P); \
     }
 
-cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+// ctas_per_sm != NULL: no launch, only the occupancy of the kernel the arguments select
+cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm)
 {
     // finv: factored +-1 LSB inverse (Haweel's T, 8-bit pixel output only)
     B200_DIRECT_CASE(MODE_RT, DT_F32, false)

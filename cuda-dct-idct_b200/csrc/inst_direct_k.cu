@@ -7,8 +7,12 @@
 namespace b200dct {
 
 template <int QM, int PIX>
-static cudaError_t launch_one(const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+static cudaError_t launch_one(const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm)
 {
+    if (ctas_per_sm) { // no launch, only the occupancy of this kernel
+        *ctas_per_sm = direct_ctas_per_sm<k_direct<MODE_RT, TK_HAWEEL, QM, PIX>>(P.zz_smem ? ZZ_SMEM_BYTES : 0);
+        return cudaSuccess;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -23,22 +27,22 @@ static cudaError_t launch_one(const DirectParams &P, dim3 grid, dim3 block, cuda
 }
 
 template <int PIX>
-static cudaError_t launch_k(int k, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+static cudaError_t launch_k(int k, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm)
 {
     switch (k) {
-    case 6: return launch_one<Q_IMM_K6, PIX>(P, grid, block, s, pdl);
-    case 7: return launch_one<Q_IMM_K7, PIX>(P, grid, block, s, pdl);
-    case 8: return launch_one<Q_IMM_K8, PIX>(P, grid, block, s, pdl);
-    case 9: return launch_one<Q_IMM_K9, PIX>(P, grid, block, s, pdl);
-    case 10: return launch_one<Q_IMM_K10, PIX>(P, grid, block, s, pdl);
+    case 6: return launch_one<Q_IMM_K6, PIX>(P, grid, block, s, pdl, ctas_per_sm);
+    case 7: return launch_one<Q_IMM_K7, PIX>(P, grid, block, s, pdl, ctas_per_sm);
+    case 8: return launch_one<Q_IMM_K8, PIX>(P, grid, block, s, pdl, ctas_per_sm);
+    case 9: return launch_one<Q_IMM_K9, PIX>(P, grid, block, s, pdl, ctas_per_sm);
+    case 10: return launch_one<Q_IMM_K10, PIX>(P, grid, block, s, pdl, ctas_per_sm);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+cudaError_t launch_direct_kmask(int k, int pix, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm)
 {
-    if (pix == DT_U8) return launch_k<DT_U8>(k, P, grid, block, s, pdl);
-    if (pix == DT_F32) return launch_k<DT_F32>(k, P, grid, block, s, pdl);
+    if (pix == DT_U8) return launch_k<DT_U8>(k, P, grid, block, s, pdl, ctas_per_sm);
+    if (pix == DT_F32) return launch_k<DT_F32>(k, P, grid, block, s, pdl, ctas_per_sm);
     return cudaErrorInvalidValue;
 }
 

@@ -247,6 +247,53 @@ def test_early_loads_never_break_dependent_call_chains(dct, oracle):
         assert torch.equal(o.view(torch.int32), w.view(torch.int32))
 
 
+@pytest.mark.parametrize("family", ["direct-u8", "direct-f32", "tma-f32"])
+def test_early_path_with_foreign_kernels_in_between(dct, oracle, family):
+    """What the CALLER enqueues between two calls is invisible to the library's host side: a foreign
+    kernel that writes the next call's input (here: torch copies / fills) must never be overtaken by the
+    early loads of that call.  The device-side completion counter decides: a launch only loads early
+    while its library predecessor is provably still running -- then nothing can stand between them.
+    Also the direct family's version of dependent chains (reads what the predecessor wrote)."""
+    N = 8192 if family != "tma-f32" else 6144   # direct family: 8192 CTAs, more than the machine holds at once
+    dt = torch.uint8 if family == "direct-u8" else torch.float32
+    plan = dct.Plan(path=dct.api.PATH_TMA if family == "tma-f32" else dct.api.PATH_DIRECT, inverse=dct.api.INVERSE_EXACT)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    src = [torch.randint(0, 256, (N, N), device="cuda", generator=g, dtype=torch.int32).to(dt) for _ in range(3)]
+    want = [dct.roundtrip(a, plan=plan).clone() for a in src]
+    want2 = dct.roundtrip(want[0], plan=plan).clone()
+    torch.cuda.synchronize()
+    band = src[0][:16].cpu().numpy()
+    got = host(want[0][:16])
+    assert np.array_equal(got, oracle.roundtrip(band)) if dt == torch.uint8 else np.array_equal(bits(got), bits(oracle.roundtrip(band)))
+    x = torch.empty_like(src[0])
+    outs = [torch.empty_like(x) for _ in range(2)]
+    bad = 0
+    for it in range(30):
+        k = it % 3
+        x.copy_(src[k])                                  # foreign kernel writes the input of the next call ...
+        dct.roundtrip(x, out=outs[it % 2], plan=plan)    # ... whose predecessor in the library's books wrote outs[(it-1) % 2]
+        if it % 5 == 4:
+            x.fill_(0)                                   # and clobbers it again right behind the call
+        bad += int(not torch.equal(outs[it % 2], want[k]))
+    assert bad == 0
+    # dependent chain: every launch reads what its predecessor wrote, and overwrites what that one read
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    for rep in range(10):
+        dct.roundtrip(src[0], out=a, plan=plan)
+        dct.roundtrip(a, out=b, plan=plan)
+        dct.roundtrip(src[0], out=a, plan=plan)          # overwrites what the previous launch is still reading
+    torch.cuda.synchronize()
+    assert torch.equal(a, want[0]) and torch.equal(b, want2)
+    # independent launches back to back (the early path proper): identical results
+    ins3, outs3 = src, [torch.empty_like(x) for _ in range(3)]
+    for rep in range(10):
+        for i in range(3):
+            dct.roundtrip(ins3[i], out=outs3[i], plan=plan)
+    torch.cuda.synchronize()
+    for o, w in zip(outs3, want):
+        assert torch.equal(o, w)
+
+
 def test_early_loads_with_threads_and_streams(dct, oracle):
     """Early tile loads are decided per (device, stream) under one lock with the launch itself: two
     host threads hammering ONE stream with dependent pairs, and two streams chained by events, stay
