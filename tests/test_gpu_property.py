@@ -294,6 +294,22 @@ def test_early_path_with_foreign_kernels_in_between(dct, oracle, family):
         assert torch.equal(o, w)
 
 
+def test_randomised_programmes_async_equals_synchronised():
+    """benchmarks/experiments/stress_early.py: random programmes of round trips (both families, in place
+    and out of place, batches) interleaved with foreign kernels that write what the next calls read; run
+    once with a device synchronisation after every operation and three times asynchronously -- every
+    buffer must end up bit-identical."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("B200DCT_INVERSE", "B200DCT_DENSE")}   # library defaults
+    r = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "experiments", "stress_early.py"), "4", "120"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "STRESS ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_early_loads_with_threads_and_streams(dct, oracle):
     """Early tile loads are decided per (device, stream) under one lock with the launch itself: two
     host threads hammering ONE stream with dependent pairs, and two streams chained by events, stay
