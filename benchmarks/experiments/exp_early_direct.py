@@ -28,6 +28,12 @@ cases = [("u8 8192^2 default", 8192, torch.uint8, m.Plan()),
          ("f32 2048^2 (auto=direct)", 2048, torch.float32, m.Plan()),
          ("f32 8192^2 dense chain direct", 8192, torch.float32, m.Plan(T=T, dense=m.api.DENSE_CHAIN)),
          ("f32 8192^2 tma (headline)", 8192, torch.float32, m.Plan())]
+rgb_in = [torch.randint(0, 256, (8192, 8192, 3), device="cuda", dtype=torch.uint8) for _ in range(3)]
+rgb_out = [torch.empty_like(x) for x in rgb_in]
+rplan = m.Plan()
+print(f"EARLY={tag} {'rgb 8192^2 (3 planes)':32s} {t(lambda i: m.roundtrip_rgb(rgb_in[i % 3], out=rgb_out[i % 3], plan=rplan), 20):8.2f} us  path={m.api.last_path()}", flush=True)
+del rgb_in, rgb_out
+torch.cuda.empty_cache()
 for name, N, dt, plan in cases:
     NP = 6 if N >= 4096 else 40
     a = [torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).to(dt) for _ in range(NP)]

@@ -30,8 +30,9 @@ def programme(seed, n_ops, kinds):
     return ops
 
 
-NBUF = {"u8": 5, "f32d": 4, "f32t": 4}
-SHAPE = {"u8": (8192, 8192, torch.uint8), "f32d": (4096, 4096, torch.float32), "f32t": (6144, 6144, torch.float32)}
+NBUF = {"u8": 5, "f32d": 4, "f32t": 4, "rgb": 4}
+SHAPE = {"u8": (8192, 8192, torch.uint8), "f32d": (4096, 4096, torch.float32), "f32t": (6144, 6144, torch.float32),
+         "rgb": (4096, 4096, 3, torch.uint8)}
 
 
 def run(ops, sync, plans, init):
@@ -41,20 +42,23 @@ def run(ops, sync, plans, init):
         kind = op[1]
         B = bufs[kind]
         if op[0] == "rt":
-            m.roundtrip(B[op[2]], out=B[op[3]], plan=plans[kind])
+            if kind == "rgb":
+                m.roundtrip_rgb(B[op[2]], out=B[op[3]], plan=plans[kind])
+            else:
+                m.roundtrip(B[op[2]], out=B[op[3]], plan=plans[kind])
         elif op[0] == "copy":
             if op[2] != op[3]:
                 B[op[3]].copy_(B[op[2]])
         elif op[0] == "fill":
             B[op[2]].fill_(op[3])
         elif op[0] == "add":
-            if kind == "u8":
+            if B[op[2]].dtype == torch.uint8:
                 B[op[2]].bitwise_xor_(B[op[3]])
             else:
                 B[op[2]].add_(B[op[3]]).clamp_(0, 255).floor_()
         elif op[0] == "batch":
             i, j = op[2], op[3]
-            if i != j:
+            if i != j and kind != "rgb":
                 m.roundtrip_batch([B[i], B[j]], outs=[B[i], B[j]], plan=plans[kind])
         if sync:
             torch.cuda.synchronize()
@@ -65,13 +69,13 @@ def run(ops, sync, plans, init):
 def main():
     trials = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     n_ops = int(sys.argv[2]) if len(sys.argv) > 2 else 250
-    plans = {"u8": m.Plan(), "f32d": m.Plan(), "f32t": m.Plan()}
+    plans = {"u8": m.Plan(), "f32d": m.Plan(), "f32t": m.Plan(), "rgb": m.Plan()}
     g = torch.Generator(device="cuda").manual_seed(3)
-    init = {k: [torch.randint(0, 256, SHAPE[k][:2], device="cuda", generator=g, dtype=torch.int32).to(SHAPE[k][2]) for _ in range(NBUF[k])]
+    init = {k: [torch.randint(0, 256, SHAPE[k][:-1], device="cuda", generator=g, dtype=torch.int32).to(SHAPE[k][-1]) for _ in range(NBUF[k])]
             for k in NBUF}
     bad = 0
     for trial in range(trials):
-        kinds = [["u8"], ["f32t"], ["f32d"], ["u8", "f32t", "f32d"]][trial % 4]
+        kinds = [["u8"], ["f32t"], ["f32d"], ["rgb"], ["u8", "f32t", "f32d", "rgb"]][trial % 5]
         ops = programme(100 + trial, n_ops, kinds)
         want = run(ops, True, plans, init)
         for rep in range(3):

@@ -7,9 +7,19 @@
 
 using namespace b200dct;
 
+// ctas_per_sm != NULL: no launch, only the occupancy of the kernel the arguments select
 template <int QK, bool FINV, bool ZZ>
-static cudaError_t launch_rgb3(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+static cudaError_t launch_rgb3(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm)
 {
+    if (ctas_per_sm) {
+        static int cached = -1;
+        if (cached < 0) {
+            int n = 0;
+            cached = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_rgb<QK, FINV, ZZ>, 128, 0) == cudaSuccess ? n : 0;
+        }
+        *ctas_per_sm = cached;
+        return cudaSuccess;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -22,9 +32,15 @@ static cudaError_t launch_rgb3(const RgbParams &P, dim3 grid, dim3 block, cudaSt
     return cudaLaunchKernelEx(&cfg, k_rgb<QK, FINV, ZZ>, P);
 }
 template <int QK, bool FINV>
-static cudaError_t launch_rgb(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl)
+static cudaError_t launch_rgb(const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm = nullptr)
 {
-    return P.zz ? launch_rgb3<QK, FINV, true>(P, grid, block, s, pdl) : launch_rgb3<QK, FINV, false>(P, grid, block, s, pdl);
+    return P.zz ? launch_rgb3<QK, FINV, true>(P, grid, block, s, pdl, ctas_per_sm) : launch_rgb3<QK, FINV, false>(P, grid, block, s, pdl, ctas_per_sm);
+}
+static cudaError_t launch_rgb_any(int qk, bool finv, const RgbParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm = nullptr)
+{
+    if (qk == 0) return finv ? launch_rgb<0, true>(P, grid, block, s, pdl, ctas_per_sm) : launch_rgb<0, false>(P, grid, block, s, pdl, ctas_per_sm);
+    if (qk == 1) return finv ? launch_rgb<1, true>(P, grid, block, s, pdl, ctas_per_sm) : launch_rgb<1, false>(P, grid, block, s, pdl, ctas_per_sm);
+    return finv ? launch_rgb<2, true>(P, grid, block, s, pdl, ctas_per_sm) : launch_rgb<2, false>(P, grid, block, s, pdl, ctas_per_sm);
 }
 
 extern "C" int b200dct_roundtrip_rgb(const b200dct_plan *plan, const void *rgb, size_t in_pitch, void *out,
@@ -60,11 +76,25 @@ extern "C" int b200dct_roundtrip_rgb(const b200dct_plan *plan, const void *rgb, 
     const bool pdl = pdl_enabled(s);
     const bool finv = use_factored_inverse_u8(plan);
     const int qk = (!plan->q_fastdiv || !plan->qc_fastdiv) ? 2 : (plan->mask == ~(uint64_t)0 ? 0 : 1);
-    forget_stream(s);
+    // early path across launch boundaries (b200dct.cu, "early loads"): a pass whose input is not written by the
+    // library's previous machine-filling launch on this stream converts and transforms before it waits
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone;
+    int per_sm = 0;
+    if (pdl && !capturing) launch_rgb_any(qk, finv, P, grid, block, s, pdl, &per_sm);
     cudaError_t e;
-    if (qk == 0) e = finv ? launch_rgb<0, true>(P, grid, block, s, pdl) : launch_rgb<0, false>(P, grid, block, s, pdl);
-    else if (qk == 1) e = finv ? launch_rgb<1, true>(P, grid, block, s, pdl) : launch_rgb<1, false>(P, grid, block, s, pdl);
-    else e = finv ? launch_rgb<2, true>(P, grid, block, s, pdl) : launch_rgb<2, false>(P, grid, block, s, pdl);
+    {
+        const Span rd{zz3_or_null ? nullptr : rgb, in_pitch, (size_t)W * 3, H};
+        const Span w0{out, out_pitch, (size_t)W * 3, H};
+        const Span w1{zz3_or_null, zz_plane_bytes, zz_bytes, 3};
+        EarlyScope scope(s, pdl && !capturing, (unsigned long long)grid.x * grid.y, per_sm, rd, w0, w1);
+        P.early = scope.params().early;
+        P.chain_feed = scope.params().chain_feed;
+        P.chain = scope.params().chain;
+        P.chain_target = scope.params().chain_target;
+        e = launch_rgb_any(qk, finv, P, grid, block, s, pdl);
+        scope.done(e == cudaSuccess);
+    }
     if (e != cudaSuccess) return (int)e;
     note_launch(1, "rgb");
     return B200DCT_OK;

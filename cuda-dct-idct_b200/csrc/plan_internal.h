@@ -24,6 +24,29 @@ struct b200dct_plan {
 
 
 namespace b200dct {
+// Early path of a hardware-scheduled (direct-style) kernel across a launch boundary, see "early loads" in
+// b200dct.cu: the scope holds the per-stream launch-order lock from the decision until done().
+struct EarlyParams {
+    int early = 0;                       // leading CTAs that may load and compute before griddepcontrol.wait
+    int chain_feed = 0;                  // trailing CTAs that add 1 to the completion counter at their end
+    unsigned long long *chain = nullptr; // completion counter of the (device, stream) record
+    unsigned long long chain_target = 0; // its value once the predecessor is complete
+};
+struct Span { const void *ptr; size_t pitch, row_bytes; int rows; };
+class EarlyScope {
+public:
+    // usable: programmatic dependent launch is on for this launch and the stream is not capturing;
+    // ctas_per_sm: occupancy of the kernel about to be launched; rd: the plane it reads (ptr NULL: never early)
+    EarlyScope(cudaStream_t s, bool usable, unsigned long long ctas, int ctas_per_sm, Span rd, Span w0, Span w1);
+    ~EarlyScope();
+    const EarlyParams &params() const { return p_; }
+    void done(bool launched);
+private:
+    EarlyParams p_;
+    void *ticket_;
+    Span w_[2];
+    bool feeds_, finished_;
+};
 void note_launch(int launches, const char *path); // b200dct_last_launch_count / b200dct_last_path of this thread
 bool use_factored_inverse_u8(const b200dct_plan *pl);
 bool pdl_enabled(cudaStream_t s);

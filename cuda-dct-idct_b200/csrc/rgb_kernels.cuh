@@ -56,6 +56,11 @@ struct RgbParams {
     void *zz;        // optional: three block-major zig-zag int16 streams (Y, Cb, Cr), zz_plane bytes apart
     size_t in_pitch, out_pitch, zz_plane, zz_pitch; // bytes; zz_pitch = bytes per block-row of one stream
     int bx, by;
+    // early path across a launch boundary (no coefficient streams only), as DirectParams: early = leading CTAs that
+    // may load and transform before griddepcontrol.wait, chain_feed = trailing CTAs that feed the counter
+    int early, chain_feed;
+    unsigned long long *chain;
+    unsigned long long chain_target;
     PlaneTables t[2]; // [0] luminance, [1] chrominance
 };
 template <bool MASKED, bool FASTDIV>
@@ -112,7 +117,16 @@ __global__ void __launch_bounds__(128, B200DCT_RGB_MIN_BLOCKS) k_rgb(const __gri
     const long long by = (long long)blockIdx.x * 4 + threadIdx.y;
     if (bxi >= P.bx || by >= P.by) return;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    bool early = false;
+    if constexpr (!ZZ) {
+        if (P.early != 0 && blockIdx.y * gridDim.x + blockIdx.x < (unsigned)P.early) { // CTA-uniform
+            __shared__ int s_early;
+            if (tid == 0) s_early = ld_counter(P.chain) < P.chain_target; // thread 0 of a CTA is always inside the image
+            __syncthreads();
+            early = s_early != 0;
+        }
+    }
+    if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- load + RGB -> YCbCr (jccolor.c rgb_ycc_convert), one row per iteration
     {
@@ -120,7 +134,9 @@ __global__ void __launch_bounds__(128, B200DCT_RGB_MIN_BLOCKS) k_rgb(const __gri
 #pragma unroll 1
         for (int r = 0; r < 8; r++) {
             const uint2 *row = reinterpret_cast<const uint2 *>(src + (size_t)r * P.in_pitch);
-            const uint2 a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
+            uint2 a, b, c;
+            if (early) a = __ldcg(row), b = __ldcg(row + 1), c = __ldcg(row + 2); // L2 only: never a stale L1 line
+            else a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
             const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
             float yv[8], cbv[8], crv[8];
             sfor<8>([&](auto k) {
@@ -155,6 +171,7 @@ __global__ void __launch_bounds__(128, B200DCT_RGB_MIN_BLOCKS) k_rgb(const __gri
     }
 
     // ---- YCbCr -> RGB (jdcolor.c ycc_rgb_convert) + store, one row per iteration
+    if (early) asm volatile("griddepcontrol.wait;" ::: "memory"); // every global write waits for the predecessor
     char *dst = (char *)P.out + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 24;
 #pragma unroll 1
     for (int r = 0; r < 8; r++) {
@@ -173,6 +190,8 @@ __global__ void __launch_bounds__(128, B200DCT_RGB_MIN_BLOCKS) k_rgb(const __gri
         row[1] = make_uint2(pack4_u8(o[8], o[9], o[10], o[11]), pack4_u8(o[12], o[13], o[14], o[15]));
         row[2] = make_uint2(pack4_u8(o[16], o[17], o[18], o[19]), pack4_u8(o[20], o[21], o[22], o[23]));
     }
+    if (P.chain_feed && tid == 0 && blockIdx.y * gridDim.x + blockIdx.x + (unsigned)P.chain_feed >= gridDim.x * gridDim.y)
+        atomicAdd(P.chain, 1ull); // one of the last CTAs of the grid is (as good as) done
 }
 
 } // namespace b200dct
