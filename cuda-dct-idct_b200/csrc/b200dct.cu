@@ -21,7 +21,7 @@ namespace b200dct {
 // one launcher per translation unit of kernel instantiations (inst_<family>_<s|d><quantiser>.cu)
 #define B200_DECL(tag)                                                                                                  \
     cudaError_t launch_direct_##tag(int mode, int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm); \
-    cudaError_t launch_direct_metrics_##tag(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s);      \
+    cudaError_t launch_direct_metrics_##tag(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm); \
     cudaError_t launch_tma_##tag(int mode, int pix, bool finv, const TmaParams &P, int grid, int block, size_t smem, cudaStream_t s, bool pdl);
 B200_DECL(s0) B200_DECL(s1) B200_DECL(s2) B200_DECL(d1) B200_DECL(d2) B200_DECL(y1) B200_DECL(y2)
 #undef B200_DECL
@@ -39,11 +39,11 @@ static cudaError_t launch_direct(int tk, int mode, int q, int pix, bool finv, co
     if (tk == TK_HAWEEL) return q == 0 ? launch_direct_s0(mode, pix, finv, P, g, b, s, pdl, c) : q == 1 ? launch_direct_s1(mode, pix, finv, P, g, b, s, pdl, c) : launch_direct_s2(mode, pix, finv, P, g, b, s, pdl, c);
     return q == 1 ? launch_direct_d1(mode, pix, finv, P, g, b, s, pdl, c) : launch_direct_d2(mode, pix, finv, P, g, b, s, pdl, c);
 }
-static cudaError_t launch_direct_metrics(int tk, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s)
+static cudaError_t launch_direct_metrics(int tk, int q, int pix, bool finv, const DirectParams &P, dim3 g, dim3 b, cudaStream_t s, bool pdl = false, int *c = nullptr)
 {
-    if (tk == TK_DENSE_SYM) return q == 1 ? launch_direct_metrics_y1(pix, finv, P, g, b, s) : launch_direct_metrics_y2(pix, finv, P, g, b, s);
-    if (tk == TK_HAWEEL) return q == 0 ? launch_direct_metrics_s0(pix, finv, P, g, b, s) : q == 1 ? launch_direct_metrics_s1(pix, finv, P, g, b, s) : launch_direct_metrics_s2(pix, finv, P, g, b, s);
-    return q == 1 ? launch_direct_metrics_d1(pix, finv, P, g, b, s) : launch_direct_metrics_d2(pix, finv, P, g, b, s);
+    if (tk == TK_DENSE_SYM) return q == 1 ? launch_direct_metrics_y1(pix, finv, P, g, b, s, pdl, c) : launch_direct_metrics_y2(pix, finv, P, g, b, s, pdl, c);
+    if (tk == TK_HAWEEL) return q == 0 ? launch_direct_metrics_s0(pix, finv, P, g, b, s, pdl, c) : q == 1 ? launch_direct_metrics_s1(pix, finv, P, g, b, s, pdl, c) : launch_direct_metrics_s2(pix, finv, P, g, b, s, pdl, c);
+    return q == 1 ? launch_direct_metrics_d1(pix, finv, P, g, b, s, pdl, c) : launch_direct_metrics_d2(pix, finv, P, g, b, s, pdl, c);
 }
 static cudaError_t launch_tma(int tk, int mode, int q, int pix, bool finv, const TmaParams &P, int g, int b, size_t smem, cudaStream_t s, bool pdl)
 {
@@ -870,10 +870,45 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     if (grid.y > 65535u) return B200DCT_ERR_SHAPE;
     cudaError_t e;
     if (partials) {
-        // fused metrics: per-CTA partials, then one fixed-order reduction into acc[0..2]
         if (mode != MODE_RT || in.ptr == out.ptr) return B200DCT_ERR_ARG;
-        forget_stream(stream);
         kmask = 0;
+        // One launch: integer sums through 64-bit atomics into the triple that belongs to a ticket-counter pair,
+        // the last CTA out folds them into acc (the TMA family's scheme).  Dependent launch and the early path apply.
+        uint32_t *slot = sched_slot(capturing);
+        unsigned long long *macc = sched_macc(slot);
+        if (slot && macc) {
+            const bool pdl = pdl_for(capturing);
+            std::lock_guard<std::mutex> launch_order(g_last_mu); // held until this kernel is in the stream
+            int per_sm = 0;
+            if (pdl && !capturing) launch_direct_metrics(pl->tk, qm, pix, finv, P, grid, block, stream, pdl, &per_sm);
+            const unsigned long long ctas = (unsigned long long)grid.x * grid.y;
+            const unsigned long long machine = (unsigned long long)per_sm * (unsigned long long)di.sms;
+            const bool fills = per_sm > 0 && ctas > machine;
+            const bool eligible = pdl && !capturing && !coef.ptr;
+            const Range rd = eligible ? plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H) : Range{};
+            const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
+            const Range w1 = plane_range(coef.ptr, coef.pitch, coef_dt == DT_I16ZZ ? (size_t)(W / 8) * 128 : (size_t)W * elem_size(coef.dt),
+                                         coef_dt == DT_I16ZZ ? H / 8 : H);
+            const Range w2 = plane_range(acc, 0, 3 * sizeof(double), 1);
+            const LaunchTicket ticket = begin_launch_locked(stream, false, fills, !capturing, rd);
+            const bool feeds = fills && ticket.chain != nullptr;
+            P.early = ticket.early ? (int)(ctas < machine ? ctas : machine) : 0;
+            P.chain = (feeds || ticket.early) ? ticket.chain : nullptr;
+            P.chain_target = ticket.target;
+            P.chain_feed = feeds ? (int)(ctas < 1024 ? ctas : 1024) : 0;
+            P.macc = macc;
+            P.mdone = slot;
+            P.acc = acc;
+            P.metrics_scale = pix == DT_U8 ? 1.0f : METRICS_FIXED_POINT;
+            e = launch_direct_metrics(pl->tk, qm, pix, finv, P, grid, block, stream, pdl);
+            if (e == cudaSuccess) commit_launch_locked(ticket, false, feeds, (unsigned long long)P.chain_feed, w0, w1, w2);
+            if (e != cudaSuccess) return (int)e;
+            tl_launches = 1;
+            tl_path = "direct";
+            return B200DCT_OK;
+        }
+        // no counter pair (capture without a free slot): per-CTA partials, then one fixed-order reduction into acc[0..2]
+        forget_stream(stream);
         P.partials = partials;
         e = launch_direct_metrics(pl->tk, qm, pix, finv, P, grid, block, stream);
         if (e != cudaSuccess) return (int)e;

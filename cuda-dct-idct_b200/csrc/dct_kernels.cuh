@@ -98,6 +98,7 @@ __device__ __forceinline__ unsigned long long ld_counter(const unsigned long lon
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+constexpr float METRICS_FIXED_POINT = 4096.0f; // f32 metrics: per-block sums are accumulated as integers in units of 2^-12
 constexpr int DIRECT_BATCH_MAX = 64; // images per launch of the batch entry point (1 KiB of kernel parameters)
 struct DirectParams {
     const void *in;   // FWD/RT: pixels (PIX dtype); INV: coefficients (coef_dt)
@@ -107,7 +108,15 @@ struct DirectParams {
     size_t in_pitch, out_pitch, coef_pitch, shifted_pitch; // bytes
     int bx, by;       // blocks per row / block rows
     int coef_dt;      // DT_F32 / DT_I16
-    double *partials; // METRICS kernels: 3 doubles per CTA {sum (x-y)^2, sum x^2, non-zero coefficients}
+    double *partials; // METRICS kernels, two-launch form: 3 doubles per CTA {sum (x-y)^2, sum x^2, non-zero coefficients}
+    // METRICS kernels, one-launch form (macc != NULL): every CTA adds its integer sums {sum (x-y)^2, sum x^2} (u8: exact
+    // integers; f32: per-block float sums in units of 2^-12, the TMA family's convention) and its non-zero count to
+    // macc[0..2] with 64-bit atomics (order-independent => deterministic); the last CTA out (mdone[1] counts them) adds
+    // the totals, divided by metrics_scale, into acc[0..2] and leaves macc and the counter zeroed
+    unsigned long long *macc;
+    uint32_t *mdone;
+    double *acc;
+    float metrics_scale;
     int zz_smem;      // 1: the launch carries ZZ_SMEM_BYTES of dynamic shared memory for the zig-zag stream transpose
     // batch of separately allocated images of one shape (b200dct_roundtrip_batch): image z of the launch
     // is blockIdx.z, its planes come from these tables instead of in / out (pixels only: no coefficient
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     // programmatic dependent launch (no-ops unless the host asked for it): see k_tma
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     bool early = false;
-    if constexpr (MODE == MODE_RT && !METRICS) {
+    if constexpr (MODE == MODE_RT) {
         if (P.early != 0 && P.coef == nullptr &&
             (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x < (unsigned)P.early) { // CTA-uniform
             __shared__ int s_early;
@@ -397,12 +406,47 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         });
     }
 
-    if constexpr (!METRICS) {
-        if (P.chain_feed && threadIdx.x == 0 && threadIdx.y == 0 &&
-            (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + (unsigned)P.chain_feed >= gridDim.x * gridDim.y * gridDim.z)
-            atomicAdd(P.chain, 1ull); // one of the last CTAs of the grid is (as good as) done
-    }
+    if (P.chain_feed && threadIdx.x == 0 && threadIdx.y == 0 &&
+        (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x + (unsigned)P.chain_feed >= gridDim.x * gridDim.y * gridDim.z)
+        atomicAdd(P.chain, 1ull); // one of the last CTAs of the grid is (as good as) done
     if constexpr (METRICS) {
+        if (P.macc) { // one-launch form
+            long long v[3] = {0, 0, 0};
+            if (valid) {
+                if constexpr (PIX == DT_U8) {
+                    v[0] = (long long)(i_xx + i_yy - 2u * i_xy);
+                    v[1] = (long long)i_xx;
+                } else {
+                    v[0] = __float2ll_rn(m_sse * METRICS_FIXED_POINT);
+                    v[1] = __float2ll_rn(m_en * METRICS_FIXED_POINT);
+                }
+                v[2] = (long long)m_nnz;
+            }
+            __shared__ long long ired[3][4];
+            const int lane = threadIdx.x, w = threadIdx.y;
+            sfor<3>([&](auto q) {
+                for (int o = 16; o > 0; o >>= 1) v[IC(q)] += __shfl_xor_sync(0xffffffffu, v[IC(q)], o);
+                if (lane == 0) ired[IC(q)][w] = v[IC(q)];
+            });
+            __syncthreads();
+            if (w == 0 && lane == 0) {
+                sfor<3>([&](auto q) {
+                    atomicAdd(&P.macc[IC(q)], (unsigned long long)((ired[IC(q)][0] + ired[IC(q)][1]) + (ired[IC(q)][2] + ired[IC(q)][3])));
+                });
+                __threadfence();
+                if (atomicAdd(&P.mdone[1], 1u) == gridDim.x * gridDim.y - 1u) { // every other CTA's sums are in
+                    __threadfence();
+                    const long long sse = (long long)atomicExch(&P.macc[0], 0ull), en = (long long)atomicExch(&P.macc[1], 0ull),
+                                    nnz = (long long)atomicExch(&P.macc[2], 0ull);
+                    P.acc[0] += (double)sse / (double)P.metrics_scale;
+                    P.acc[1] += (double)en / (double)P.metrics_scale;
+                    P.acc[2] += (double)nnz;
+                    P.mdone[1] = 0;
+                    __threadfence();
+                }
+            }
+            return;
+        }
         if constexpr (PIX == DT_U8) {
             m_sse = (float)(i_xx + i_yy - 2u * i_xy);
             m_en = (float)i_xx;
@@ -474,7 +518,6 @@ struct TmaParams {
     uint32_t bx;          // blocks per image row (lanes of a right-edge tile beyond it hold TMA zero fill, not pixels)
     CommonParams cp;
 };
-constexpr float METRICS_FIXED_POINT = 4096.0f;
 
 // every warp owns two tile buffers (in, out) of P.buf_bytes each: 8 KiB when an f32 plane is
 // involved, 4 KiB for i16, 2 KiB for an all-u8 round trip

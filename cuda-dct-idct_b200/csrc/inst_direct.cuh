@@ -54,24 +54,33 @@ cudaError_t B200_CAT(launch_direct_, INST_TAG)(int mode, int pix, bool finv, con
 #endif
 }
 
-cudaError_t B200_CAT(launch_direct_metrics_, INST_TAG)(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s)
+#define B200_METRICS_CASE(X, F)                                                     \
+    if (pix == (X) && finv == (F)) {                                                \
+        if (ctas_per_sm) {                                                          \
+            *ctas_per_sm = direct_ctas_per_sm<k_direct<MODE_RT, INST_SPARSE, INST_Q, X, true, F>>(0); \
+            return cudaSuccess;                                                     \
+        }                                                                           \
+        cudaLaunchConfig_t cfg = {};                                                \
+        cfg.gridDim = grid;                                                         \
+        cfg.blockDim = block;                                                       \
+        cfg.stream = s;                                                             \
+        cudaLaunchAttribute attr[1];                                                \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;            \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                     \
+        cfg.attrs = attr;                                                           \
+        cfg.numAttrs = pdl ? 1 : 0;                                                 \
+        return cudaLaunchKernelEx(&cfg, k_direct<MODE_RT, INST_SPARSE, INST_Q, X, true, F>, P); \
+    }
+
+// ctas_per_sm != NULL: no launch, only the occupancy of the kernel the arguments select
+cudaError_t B200_CAT(launch_direct_metrics_, INST_TAG)(int pix, bool finv, const DirectParams &P, dim3 grid, dim3 block, cudaStream_t s, bool pdl, int *ctas_per_sm)
 {
 #ifndef B200DCT_FAST_BUILD
 #if INST_SPARSE == 1
-    if (pix == DT_U8 && finv) {
-        k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_U8, true, true><<<grid, block, 0, s>>>(P);
-        return cudaGetLastError();
-    }
+    B200_METRICS_CASE(DT_U8, true)
 #endif
-    if (finv) return cudaErrorInvalidValue;
-    if (pix == DT_F32) {
-        k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_F32, true><<<grid, block, 0, s>>>(P);
-        return cudaGetLastError();
-    }
-    if (pix == DT_U8) {
-        k_direct<MODE_RT, INST_SPARSE, INST_Q, DT_U8, true><<<grid, block, 0, s>>>(P);
-        return cudaGetLastError();
-    }
+    B200_METRICS_CASE(DT_F32, false)
+    B200_METRICS_CASE(DT_U8, false)
 #endif
     return cudaErrorInvalidValue;
 }

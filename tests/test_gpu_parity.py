@@ -599,6 +599,14 @@ def test_fused_metrics_tma_family(dct, oracle, shape):
         assert len(seen) == 1, "fixed-point accumulation must not depend on the tile schedule"
     # accumulating calls ADD into the caller's accumulators on both families
     x = dev(img)
+    both = {}
     for path in ("tma", "direct"):
-        _, (m1, _, n1) = dct.roundtrip_with_metrics(x, plan=dct.Plan(path=PATHS[path]))
+        _, (m1, p1, n1) = dct.roundtrip_with_metrics(x, plan=dct.Plan(path=PATHS[path]))
         assert m1 == pytest.approx(oracle.metrics(img, oracle.roundtrip(img))[0], rel=1e-6)
+        assert dct.api.last_path() == path and dct.api.last_launch_count() == 1   # one launch on both families
+        both[path] = (m1, p1, n1)
+    # same per-block float sums, same 2^-12 fixed point, integer accumulation: the families agree bit for bit
+    assert both["tma"] == both["direct"]
+    # and the direct family's integer accumulation does not depend on the CTA schedule either
+    seen = {dct.roundtrip_with_metrics(x, plan=dct.Plan(path=PATHS["direct"]))[1] for _ in range(4)}
+    assert len(seen) == 1
