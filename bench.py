@@ -612,7 +612,7 @@ def extras_multi_gpu(m, dev, rank, world):
     # the alternative form of configs[4]: a batch of 64 separately allocated 8192^2 u8 images, image b on
     # rank b mod world, every rank ONE batch call; strong scaling, no collective
     nb, side = 64, 8192
-    mine = list(range(rank, nb, world))
+    mine = m.batch_images(nb, world, rank)
     gb = torch.Generator(device=dev).manual_seed(2000 + rank)
     batch = m.ImageBatch([torch.randint(0, 256, (side, side), device=dev, generator=gb, dtype=torch.uint8) for _ in mine])
 

@@ -19,3 +19,14 @@ def stripe_rows(H: int, world_size: int, rank: int) -> tuple[int, int]:
     b0 = rank * base + min(rank, extra)
     b1 = b0 + base + (1 if rank < extra else 0)
     return b0 * 8, b1 * 8
+
+
+def batch_images(n_images: int, world_size: int, rank: int) -> list[int]:
+    """Indices of the images of a batch that `rank` processes: image b goes to rank b mod world_size
+    (BASELINE configs[4] "a batch of 64 8192^2 images"); every image exactly once,
+    counts differ by at most one, empty shares allowed."""
+    if n_images < 0:
+        raise ValueError("n_images must not be negative")
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    return list(range(rank, n_images, world_size))

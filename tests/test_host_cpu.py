@@ -126,6 +126,17 @@ def test_product_never_imports_oracle():
         assert "liboracle" not in open(os.path.join(ROOT, "include", f)).read()
 
 
+def test_batch_images(m):
+    for n in (0, 1, 7, 64, 65):
+        for ws in (1, 2, 3, 8):
+            shares = [m.batch_images(n, ws, r) for r in range(ws)]
+            assert sorted(i for s in shares for i in s) == list(range(n))        # every image exactly once
+            assert max(map(len, shares)) - min(map(len, shares)) <= 1
+            assert all(i % ws == r for r, s in enumerate(shares) for i in s)     # image b on rank b mod world
+    with pytest.raises(ValueError):
+        m.batch_images(4, 2, 2)
+
+
 def test_stripe_rows(m):
     for H in (8, 64, 8192, 32768, 72):
         for ws in (1, 2, 3, 4, 8, 16):
