@@ -592,7 +592,7 @@ void forget_stream(cudaStream_t s)
 }
 // the same protocol for the direct-style kernels of other translation units (colour)
 EarlyScope::EarlyScope(cudaStream_t s, bool usable, unsigned long long ctas, int ctas_per_sm, Span rd, Span w0, Span w1)
-    : ticket_(nullptr), feeds_(false), finished_(false)
+    : rec_(nullptr), feeds_(false), finished_(false)
 {
     g_last_mu.lock();
     w_[0] = w0;
@@ -602,23 +602,23 @@ EarlyScope::EarlyScope(cudaStream_t s, bool usable, unsigned long long ctas, int
     const unsigned long long machine = (unsigned long long)(ctas_per_sm > 0 ? ctas_per_sm : 0) * (unsigned long long)sms;
     const bool fills = usable && machine > 0 && ctas > machine;
     const Range r = (usable && rd.ptr) ? plane_range(rd.ptr, rd.pitch, rd.row_bytes, rd.rows) : Range{};
-    LaunchTicket *t = new LaunchTicket(begin_launch_locked(s, false, fills, usable, r));
-    ticket_ = t;
-    feeds_ = fills && t->chain != nullptr;
-    p_.early = t->early ? (int)(ctas < machine ? ctas : machine) : 0;
-    p_.chain = (feeds_ || t->early) ? t->chain : nullptr;
-    p_.chain_target = t->target;
+    const LaunchTicket t = begin_launch_locked(s, false, fills, usable, r);
+    rec_ = t.rec;
+    feeds_ = fills && t.chain != nullptr;
+    p_.early = t.early ? (int)(ctas < machine ? ctas : machine) : 0;
+    p_.chain = (feeds_ || t.early) ? t.chain : nullptr;
+    p_.chain_target = t.target;
     p_.chain_feed = feeds_ ? (int)(ctas < 1024 ? ctas : 1024) : 0;
 }
 void EarlyScope::done(bool launched)
 {
     if (finished_) return;
     finished_ = true;
-    LaunchTicket *t = static_cast<LaunchTicket *>(ticket_);
+    LaunchTicket t;
+    t.rec = static_cast<LastLaunch *>(rec_);
     if (launched)
-        commit_launch_locked(*t, false, feeds_, (unsigned long long)p_.chain_feed, plane_range(w_[0].ptr, w_[0].pitch, w_[0].row_bytes, w_[0].rows),
+        commit_launch_locked(t, false, feeds_, (unsigned long long)p_.chain_feed, plane_range(w_[0].ptr, w_[0].pitch, w_[0].row_bytes, w_[0].rows),
                              plane_range(w_[1].ptr, w_[1].pitch, w_[1].row_bytes, w_[1].rows));
-    delete t;
     g_last_mu.unlock();
 }
 EarlyScope::~EarlyScope() { done(false); }

@@ -43,7 +43,7 @@ public:
     void done(bool launched);
 private:
     EarlyParams p_;
-    void *ticket_;
+    void *rec_;    // the (device, stream) record of b200dct.cu
     Span w_[2];
     bool feeds_, finished_;
 };
