@@ -458,15 +458,16 @@ unsigned long long *sched_macc(const uint32_t *slot)
 // written by the launch it can overlap with, its loads need not wait -- only its writes do.  The
 // library establishes that by itself, per (device, stream):
 //   * the relaxation only ever applies to the immediately preceding kernel of the stream, and only if
-//     that kernel triggers launch_dependents -- i.e. one of this library's; anything else the caller
-//     enqueues in between (copies, other kernels) restores full stream order by itself;
+//     that kernel triggers launch_dependents -- i.e. one of this library's; what the caller enqueues in
+//     between (copies, other kernels) cannot be seen from here and is excluded on the device by the
+//     completion counter described further down;
 //   * when that predecessor is a persistent TMA-family launch that fills the machine (a CTA on every SM)
 //     and both launches take more than half of an SM's shared memory (so they can never share an SM),
 //     a successor CTA starts only where a predecessor CTA has EXITED, which it cannot do before
 //     having passed its own wait: everything older than the predecessor is complete by the time a
 //     successor CTA runs, and only the predecessor's writes matter;
-//   * so: predecessor on this stream = TMA family, and [input plane] disjoint from its output /
-//     coefficient planes  =>  early_loads.  Every other launch of the library clears the record.
+//   * so: predecessor on this stream = such a launch, and [input plane] disjoint from its output /
+//     coefficient planes  =>  early_loads.  Launches that do not qualify as predecessors clear the record.
 // Not under stream capture.  env B200DCT_EARLY_LOADS=0 disables (A/B).
 namespace {
 struct Range {
