@@ -546,6 +546,37 @@ def extras_single_gpu(m, dev, peak):
         ex[key] = entry(ms, N2 * N2, 8, what=what, kernel_path=m.api.last_path())
     del a, b
     torch.cuda.empty_cache()
+    # MSE / PEEN / non-zero count from the same pass (one launch on either family), and 8(f4): images
+    # whose sides are not multiples of 8 and whose rows are not aligned (one pass of the edge-replicating kernels)
+    import ctypes as C
+    L = m.lib()
+    for key, dt, code, es, bpp in (("metrics_f32_8192", torch.float32, 0, 4, 8), ("metrics_u8_8192", torch.uint8, 1, 1, 2)):
+        xs = [torch.randint(0, 256, (N, N), device=dev, dtype=torch.int32).to(dt) for _ in range(3)]
+        ys = [torch.empty_like(x) for x in xs]
+        nb = int(L.b200dct_metrics_workspace_bytes(N, N))
+        ws = torch.empty(max(1, nb // 8), dtype=torch.float64, device=dev)
+        acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        sp, plan_m = C.c_void_p(stream.cuda_stream), m.Plan()
+
+        def mstep(i):
+            m.api._check(L.b200dct_roundtrip_metrics(plan_m._h, xs[i % 3].data_ptr(), code, N * es, ys[i % 3].data_ptr(), code, N * es,
+                                                     None, 0, 0, N, N, acc.data_ptr(), ws.data_ptr(), nb, sp))
+        ms = time_config(m, mstep)
+        ex[key] = entry(ms, N * N, bpp, launches=m.api.last_launch_count(), kernel_path=m.api.last_path(),
+                        what="b200dct_roundtrip_metrics: fused round trip that also accumulates sum (x-y)^2, sum x^2 and the non-zero coefficient count")
+        del xs, ys, ws
+    M1 = N - 1
+    for key, dt, bpp in (("any_f32_8191", torch.float32, 8), ("any_u8_8191", torch.uint8, 2)):
+        xs = [torch.randint(0, 256, (M1, M1), device=dev, dtype=torch.int32).to(dt) for _ in range(3)]
+        ys = [torch.empty_like(x) for x in xs]
+        plan_a = m.Plan()
+
+        def astep(i):
+            m.roundtrip_any(xs[i % 3], out=ys[i % 3], plan=plan_a, stream=stream)
+        ex[key] = entry(time_config(m, astep), M1 * M1, bpp, kernel_path=m.api.last_path(),
+                        what="b200dct_roundtrip_any on an 8191 x 8191 image (sides not multiples of 8, rows unaligned): edge replication, one pass, no scratch image")
+        del xs, ys
+    torch.cuda.empty_cache()
     # batches of SEPARATELY ALLOCATED images in one launch per 64 images (b200dct_roundtrip_batch) against
     # the loop of single-image calls a caller of the reference writes; the 64 x 8192^2 u8 batch is the
     # alternative form of BASELINE configs[4] on one GPU
