@@ -313,15 +313,17 @@ def test_randomised_programmes_async_equals_synchronised():
     assert r.returncode == 0 and "STRESS ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_early_loads_with_threads_and_streams(dct, oracle):
-    """Early tile loads are decided per (device, stream) under one lock with the launch itself: two
+@pytest.mark.parametrize("family", ["tma-f32", "direct-u8"])
+def test_early_loads_with_threads_and_streams(dct, oracle, family):
+    """The early path is decided per (device, stream) under one lock with the launch itself: two
     host threads hammering ONE stream with dependent pairs, and two streams chained by events, stay
-    exact."""
+    exact (TMA family: early tile loads; direct family: load + transform before the wait)."""
     import threading
 
-    N = 6144
-    x = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32).float()
-    plan = dct.Plan()
+    N = 6144 if family == "tma-f32" else 8192
+    x = torch.randint(0, 256, (N, N), device="cuda", dtype=torch.int32)
+    x = x.float() if family == "tma-f32" else x.to(torch.uint8)
+    plan = dct.Plan(inverse=dct.api.INVERSE_EXACT)
     want1 = dct.roundtrip(x, plan=plan).clone()
     want2 = dct.roundtrip(want1, plan=plan).clone()
     torch.cuda.synchronize()
