@@ -30,9 +30,9 @@ def programme(seed, n_ops, kinds):
     return ops
 
 
-NBUF = {"u8": 5, "f32d": 4, "f32t": 4, "rgb": 4}
+NBUF = {"u8": 5, "f32d": 4, "f32t": 4, "rgb": 4, "anyf": 4}
 SHAPE = {"u8": (8192, 8192, torch.uint8), "f32d": (4096, 4096, torch.float32), "f32t": (6144, 6144, torch.float32),
-         "rgb": (4096, 4096, 3, torch.uint8)}
+         "rgb": (4096, 4096, 3, torch.uint8), "anyf": (6001, 6007, torch.float32)}
 
 
 def run(ops, sync, plans, init):
@@ -44,6 +44,8 @@ def run(ops, sync, plans, init):
         if op[0] == "rt":
             if kind == "rgb":
                 m.roundtrip_rgb(B[op[2]], out=B[op[3]], plan=plans[kind])
+            elif kind == "anyf":
+                m.roundtrip_any(B[op[2]], out=B[op[3]], plan=plans[kind])
             else:
                 m.roundtrip(B[op[2]], out=B[op[3]], plan=plans[kind])
         elif op[0] == "copy":
@@ -58,7 +60,7 @@ def run(ops, sync, plans, init):
                 B[op[2]].add_(B[op[3]]).clamp_(0, 255).floor_()
         elif op[0] == "batch":
             i, j = op[2], op[3]
-            if i != j and kind != "rgb":
+            if i != j and kind not in ("rgb", "anyf"):
                 m.roundtrip_batch([B[i], B[j]], outs=[B[i], B[j]], plan=plans[kind])
         if sync:
             torch.cuda.synchronize()
@@ -69,13 +71,13 @@ def run(ops, sync, plans, init):
 def main():
     trials = int(sys.argv[1]) if len(sys.argv) > 1 else 6
     n_ops = int(sys.argv[2]) if len(sys.argv) > 2 else 250
-    plans = {"u8": m.Plan(), "f32d": m.Plan(), "f32t": m.Plan(), "rgb": m.Plan()}
+    plans = {"u8": m.Plan(), "f32d": m.Plan(), "f32t": m.Plan(), "rgb": m.Plan(), "anyf": m.Plan()}
     g = torch.Generator(device="cuda").manual_seed(3)
     init = {k: [torch.randint(0, 256, SHAPE[k][:-1], device="cuda", generator=g, dtype=torch.int32).to(SHAPE[k][-1]) for _ in range(NBUF[k])]
             for k in NBUF}
     bad = 0
     for trial in range(trials):
-        kinds = [["u8"], ["f32t"], ["f32d"], ["rgb"], ["u8", "f32t", "f32d", "rgb"]][trial % 5]
+        kinds = [["u8"], ["f32t"], ["f32d"], ["rgb"], ["anyf"], ["u8", "f32t", "f32d", "rgb", "anyf"]][trial % 6]
         ops = programme(100 + trial, n_ops, kinds)
         want = run(ops, True, plans, init)
         for rep in range(3):

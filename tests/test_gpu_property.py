@@ -308,7 +308,7 @@ def test_randomised_programmes_async_equals_synchronised():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = {k: v for k, v in os.environ.items() if k not in ("B200DCT_INVERSE", "B200DCT_DENSE")}   # library defaults
-    r = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "experiments", "stress_early.py"), "5", "120"],
+    r = subprocess.run([sys.executable, os.path.join(root, "benchmarks", "experiments", "stress_early.py"), "6", "100"],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "STRESS ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
