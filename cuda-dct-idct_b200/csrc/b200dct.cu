@@ -661,6 +661,14 @@ bool pdl_enabled(cudaStream_t s)
 }
 } // namespace b200dct
 static int tma_grid = 0;                          // env B200DCT_TMA_GRID: CTAs (default: one per SM)
+static bool direct_v8() // env B200DCT_DIRECT_V8=0: no 256-bit global accesses in the direct family (A/B)
+{
+    static const bool v = [] {
+        const char *p = getenv("B200DCT_DIRECT_V8");
+        return !(p && atoi(p) == 0);
+    }();
+    return v;
+}
 static bool compiled_masks() // env B200DCT_COMPILED_MASKS=0: retained-coefficient masks as runtime data only (A/B)
 {
     static const bool v = [] {
@@ -865,6 +873,10 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
     P.bx = W / 8; P.by = H / 8;
     P.coef_dt = coef_dt;
     P.zz_smem = (coef_dt == DT_I16ZZ && !partials) ? 1 : 0; // the metrics kernels are launched without dynamic smem
+    if (direct_v8()) { // f32 planes aligned to 32 bytes move with 256-bit accesses
+        auto aligned32 = [](const Plane &pl) { return pl.ptr && pl.dt == DT_F32 && !((uintptr_t)pl.ptr & 31) && !(pl.pitch & 31); };
+        P.v8 = (aligned32(in) ? 1 : 0) | (aligned32(out) ? 2 : 0) | (aligned32(coef) ? 4 : 0);
+    }
     P.cp = pl->cp;
     dim3 block(32, 4);
     dim3 grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32));
@@ -1030,6 +1042,9 @@ extern "C" int b200dct_roundtrip_batch(const b200dct_plan *plan, int n_images, c
     P.bx = W / 8; P.by = H / 8;
     P.coef_dt = DT_F32;
     P.cp = plan->cp;
+    bool v8 = dt == B200DCT_F32 && direct_v8() && !(in_pitch & 31) && !(out_pitch & 31);
+    for (int i = 0; v8 && i < n_images; i++) v8 = !((uintptr_t)imgs[i] & 31) && !((uintptr_t)outs[i] & 31);
+    P.v8 = v8 ? 3 : 0;
     dim3 block(32, 4);
     dim3 grid((unsigned)((P.by + 3) / 4), (unsigned)((P.bx + 31) / 32), 1);
     if (grid.y > 65535u) return B200DCT_ERR_SHAPE;

@@ -122,6 +122,9 @@ struct DirectParams {
     // is blockIdx.z, its planes come from these tables instead of in / out (pixels only: no coefficient
     // plane, no side effect, no metrics); 0 = the single image above
     int nimg;
+    // f32 planes that are 32-byte aligned in address and pitch move with 256-bit accesses: bit 0 = the input plane
+    // (all inputs of a batch), bit 1 = the output plane, bit 2 = the optional coefficient plane of a round trip
+    int v8;
     // early (fused round trips without coefficient plane only): the host has established that nothing this
     // launch READS is written by the launch it may overlap with (see early loads, b200dct.cu): the block is
     // loaded (L2-coherent loads) and transformed before griddepcontrol.wait, only the stores wait for the
@@ -158,6 +161,23 @@ __device__ __forceinline__ void ld_row_f32_cg(const void *base, float2 (&r)[4]) 
     const float4 b = __ldcg(reinterpret_cast<const float4 *>(base) + 1);
     r[0] = make_float2(a.x, a.y); r[1] = make_float2(a.z, a.w);
     r[2] = make_float2(b.x, b.y); r[3] = make_float2(b.z, b.w);
+}
+// 256-bit accesses (sm_100: LDG.E.256 / STG.E.256): a lane's whole 32-byte block row -- one full sector -- per
+// instruction instead of two half-sector 128-bit accesses; rows must be 32-byte aligned (P.v8).
+template <bool CG>
+__device__ __forceinline__ void ld_row_f32_v8(const void *base, float2 (&r)[4])
+{
+    if constexpr (CG)
+        asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y) : "l"(base) : "memory");
+    else
+        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r[0].x), "=f"(r[0].y), "=f"(r[1].x), "=f"(r[1].y), "=f"(r[2].x), "=f"(r[2].y), "=f"(r[3].x), "=f"(r[3].y) : "l"(base) : "memory");
+}
+__device__ __forceinline__ void st_row_f32_v8(void *base, const float2 (&r)[4])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(base), "f"(r[0].x), "f"(r[0].y), "f"(r[1].x), "f"(r[1].y),
+                 "f"(r[2].x), "f"(r[2].y), "f"(r[3].x), "f"(r[3].y) : "memory");
 }
 __device__ __forceinline__ void st_row_f32(void *base, const float2 (&r)[4])
 {
@@ -312,7 +332,8 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     if constexpr (MODE == MODE_INV) {
         const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch;
         if (P.coef_dt == DT_F32) {
-            sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+            if (P.v8 & 1) sfor<8>([&](auto r) { ld_row_f32_v8<false>(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+            else sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
         } else if (P.coef_dt == DT_I16ZZ) { // pitch = bytes per block-row of the stream
             const char *row = (const char *)in_plane + (size_t)by * P.in_pitch;
             if (zz_coop) ld_warp_zigzag(row + (size_t)blockIdx.y * 4096, zz_buf, threadIdx.x, p);
@@ -324,7 +345,9 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         }
     } else if constexpr (PIX == DT_F32) {
         const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
-        if (early) sfor<8>([&](auto r) { ld_row_f32_cg(src + IC(r) * P.in_pitch, p[IC(r)]); });
+        if ((P.v8 & 1) && early) sfor<8>([&](auto r) { ld_row_f32_v8<true>(src + IC(r) * P.in_pitch, p[IC(r)]); });
+        else if (P.v8 & 1) sfor<8>([&](auto r) { ld_row_f32_v8<false>(src + IC(r) * P.in_pitch, p[IC(r)]); });
+        else if (early) sfor<8>([&](auto r) { ld_row_f32_cg(src + IC(r) * P.in_pitch, p[IC(r)]); });
         else sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch, p[IC(r)]); });
         sfor<8>([&](auto r) { shift_row(p[IC(r)], -128.0f); }); // sub_matrix_scalar, utils_kernels.cu:16
         if constexpr (MODE == MODE_FWD) {
@@ -341,10 +364,11 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
         sfor<8>([&](auto r) { unpack_u8_shifted(w[IC(r)], p[IC(r)]); });
     }
 
-    auto store_coef = [&](void *plane, size_t pitch, float2 (&c)[8][4]) {
+    auto store_coef = [&](void *plane, size_t pitch, bool v8, float2 (&c)[8][4]) {
         char *dst = (char *)plane + (size_t)by * 8 * pitch;
         if (P.coef_dt == DT_F32) {
-            sfor<8>([&](auto r) { st_row_f32(dst + IC(r) * pitch + (size_t)bxi * 32, c[IC(r)]); });
+            if (v8) sfor<8>([&](auto r) { st_row_f32_v8(dst + IC(r) * pitch + (size_t)bxi * 32, c[IC(r)]); });
+            else sfor<8>([&](auto r) { st_row_f32(dst + IC(r) * pitch + (size_t)bxi * 32, c[IC(r)]); });
         } else if (P.coef_dt == DT_I16ZZ) {
             char *row = (char *)plane + (size_t)by * pitch;
             if (zz_coop) st_warp_zigzag(row + (size_t)blockIdx.y * 4096, zz_buf, threadIdx.x, c);
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     };
 
     run_block<MODE, TK, QMODE, true, FINV>(p, P.cp, [&](float2 (&c)[8][4]) {
-        if (P.coef && valid) store_coef(P.coef, P.coef_pitch, c);
+        if (P.coef && valid) store_coef(P.coef, P.coef_pitch, (P.v8 & 4) != 0, c);
         if constexpr (METRICS) {
             sfor<8>([&](auto r) {
                 sfor<4>([&](auto j) {
@@ -372,13 +396,16 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     if (early) asm volatile("griddepcontrol.wait;" ::: "memory"); // every global write waits for the predecessor
     void *const out_plane = P.nimg ? P.img_out[blockIdx.z] : P.out;
     if constexpr (MODE == MODE_FWD) {
-        store_coef(out_plane, P.out_pitch, p);
+        store_coef(out_plane, P.out_pitch, (P.v8 & 2) != 0, p);
     } else if constexpr (PIX == DT_F32) {
         char *dst = (char *)out_plane + (size_t)by * 8 * P.out_pitch + (size_t)bxi * 32;
         const char *src = (const char *)P.in + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
         sfor<8>([&](auto r) {
             if constexpr (!BIASED) shift_row(p[IC(r)], 128.0f); // add_matrix_scalar, utils_kernels.cu:29
-            if (valid) st_row_f32(dst + IC(r) * P.out_pitch, p[IC(r)]);
+            if (valid) {
+                if (P.v8 & 2) st_row_f32_v8(dst + IC(r) * P.out_pitch, p[IC(r)]);
+                else st_row_f32(dst + IC(r) * P.out_pitch, p[IC(r)]);
+            }
             if constexpr (METRICS) {
                 float2 x[4];
                 ld_row_f32(src + IC(r) * P.in_pitch, x);
