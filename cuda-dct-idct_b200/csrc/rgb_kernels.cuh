@@ -86,6 +86,35 @@ __device__ __forceinline__ float row_byte(const uint32_t (&w)[6])
 {
     return u8_to_float(w[J >> 2], J & 3);
 }
+// ---- RGB -> YCbCr on the integer dot-product unit (IDP.2A: two 16-bit x 8-bit products per instruction).
+// libjpeg's expressions are sums of 16-bit constants times 8-bit samples, which is exactly what dp2a computes:
+// with the pixel's bytes {R, G, B, x} in one word, .lo multiplies (R, G) and .hi (B, x) by the two halves of the
+// constant word.  7 instructions per pixel instead of 6 byte-to-float conversions + 9 FMA + 3 floors; the sample
+// is byte 2 of the 32-bit result (every result is in [0, 2^24)).  FIX(0.5) = 32768 does not fit a signed 16-bit
+// half, so it travels as an unsigned half next to a zero (Cb) or negated as -32768 (Cr, whose sum is subtracted).
+#define B200_IFIX(x) ((int)((x) * 65536.0 + 0.5))
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t dp2a_hi_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_lo_su(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_su(uint32_t a, uint32_t b, int c) { int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__host__ __device__ constexpr uint32_t halves(int lo, int hi) { return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16); }
+// pixel word {R, G, B, x} -> the three 32-bit sums whose byte 2 is Y, Cb, Cr (jccolor.c rgb_ycc_convert)
+__device__ __forceinline__ void rgb_to_ycc_sums(uint32_t w, uint32_t &y, uint32_t &cb, uint32_t &cr)
+{
+    constexpr int ONE_HALF = 1 << 15, CBCR = (128 << 16) + ONE_HALF - 1; // CBCR_OFFSET + ONE_HALF - 1
+    y = dp2a_hi_uu(halves(B200_IFIX(0.11400), 0), w, dp2a_lo_uu(halves(B200_IFIX(0.29900), B200_IFIX(0.58700)), w, (uint32_t)ONE_HALF));
+    cb = dp2a_hi_uu(halves(32768, 0), w, (uint32_t)dp2a_lo_su(halves(-B200_IFIX(0.16874), -B200_IFIX(0.33126)), w, CBCR));
+    // Cr = CBCR + 32768 R - FIX(0.41869) G - FIX(0.08131) B = CBCR - (-32768 R + FIX(0.41869) G + FIX(0.08131) B)
+    cr = (uint32_t)(CBCR - dp2a_hi_su(halves(B200_IFIX(0.08131), 0), w, dp2a_lo_su(halves(-32768, B200_IFIX(0.41869)), w, 0)));
+}
+// byte 2 of eight 32-bit sums as eight packed bytes
+__device__ __forceinline__ uint2 pack_byte2(const uint32_t (&v)[8])
+{
+    uint2 o;
+    o.x = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+    o.y = __byte_perm(__byte_perm(v[4], v[5], 0x0062), __byte_perm(v[6], v[7], 0x0062), 0x5410);
+    return o;
+}
 // the low mantissa bytes of eight MAGIC-biased floats as eight packed bytes
 __device__ __forceinline__ uint2 pack_magic_bytes(const float (&v)[8])
 {
@@ -138,18 +167,15 @@ __global__ void __launch_bounds__(128, B200DCT_RGB_MIN_BLOCKS) k_rgb(const __gri
             if (early) a = __ldcg(row), b = __ldcg(row + 1), c = __ldcg(row + 2); // L2 only: never a stale L1 line
             else a = __ldg(row), b = __ldg(row + 1), c = __ldg(row + 2);
             const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
-            float yv[8], cbv[8], crv[8];
-            sfor<8>([&](auto k) {
-                const float R = row_byte<3 * IC(k)>(w), G = row_byte<3 * IC(k) + 1>(w), B = row_byte<3 * IC(k) + 2>(w);
-                // every partial sum is an integer multiple of 2^-16 below 2^8: exact; the low mantissa byte
-                // of MAGIC + floor(.) is the sample
-                yv[IC(k)] = floor_magic(__fmaf_rn(R, B200_FIX(0.29900), __fmaf_rn(G, B200_FIX(0.58700), __fmaf_rn(B, B200_FIX(0.11400), 0.5f))));
-                cbv[IC(k)] = floor_magic(__fmaf_rn(R, -B200_FIX(0.16874), __fmaf_rn(G, -B200_FIX(0.33126), __fmaf_rn(B, 0.5f, 128.0f + 32767.0f / 65536.0f))));
-                crv[IC(k)] = floor_magic(__fmaf_rn(R, 0.5f, __fmaf_rn(G, -B200_FIX(0.41869), __fmaf_rn(B, -B200_FIX(0.08131), 128.0f + 32767.0f / 65536.0f))));
-            });
-            park[0][r][tid] = pack_magic_bytes(yv);
-            park[1][r][tid] = pack_magic_bytes(cbv);
-            park[2][r][tid] = pack_magic_bytes(crv);
+            // pixel k occupies bytes 3k .. 3k+2 of the 24-byte row: {R, G, B, next byte} as one word (the
+            // fourth byte meets a zero constant)
+            const uint32_t px[8] = {w[0], __byte_perm(w[0], w[1], 0x6543), __byte_perm(w[1], w[2], 0x5432), w[2] >> 8,
+                                    w[3], __byte_perm(w[3], w[4], 0x6543), __byte_perm(w[4], w[5], 0x5432), w[5] >> 8};
+            uint32_t yv[8], cbv[8], crv[8];
+            sfor<8>([&](auto k) { rgb_to_ycc_sums(px[IC(k)], yv[IC(k)], cbv[IC(k)], crv[IC(k)]); });
+            park[0][r][tid] = pack_byte2(yv);
+            park[1][r][tid] = pack_byte2(cbv);
+            park[2][r][tid] = pack_byte2(crv);
         }
     }
 
