@@ -17,12 +17,13 @@
 // and stored.  24 KiB of shared memory per 128-thread CTA, no barrier (every thread only ever
 // touches its own slots).
 //
-// The fixed-point colour arithmetic runs on the FP32 pipe, exactly: every product and partial sum
+// The forward conversion runs on the integer dot-product unit (IDP.2A, see rgb_to_ycc_sums).  The inverse
+// conversion's constants need 17 bits, so it runs on the FP32 pipe, exactly: every product and partial sum
 // of the libjpeg expressions is an integer of magnitude < 2^24 (e.g. 255 * 65536 + 32768), the
 // coefficients are pre-scaled by 2^-16 (a pure exponent shift), so each FMA is exact and
 // ">> 16" (arithmetic) is a round-toward-minus-infinity to integer, done by adding 1.5 * 2^23 in
-// RM mode.  Bit-identical to the integer code (tests/test_gpu_rgb.py against the CPU restatement, which is
-// pinned against the real libjpeg).
+// RM mode.  Both are bit-identical to the integer code (tests/test_gpu_rgb.py against the CPU restatement,
+// which is pinned against the real libjpeg).
 #pragma once
 
 #include "dct_kernels.cuh"
@@ -80,12 +81,6 @@ constexpr float RGB_MAGIC = 12582912.0f; // 1.5 * 2^23: x + MAGIC in RM mode = M
 
 __device__ __forceinline__ float floor_magic(float x) { return __fadd_rd(x, RGB_MAGIC); } // MAGIC + floor(x)
 
-// byte j (0..23) of a 24-byte row held in six 32-bit words, as float
-template <int J>
-__device__ __forceinline__ float row_byte(const uint32_t (&w)[6])
-{
-    return u8_to_float(w[J >> 2], J & 3);
-}
 // ---- RGB -> YCbCr on the integer dot-product unit (IDP.2A: two 16-bit x 8-bit products per instruction).
 // libjpeg's expressions are sums of 16-bit constants times 8-bit samples, which is exactly what dp2a computes:
 // with the pixel's bytes {R, G, B, x} in one word, .lo multiplies (R, G) and .hi (B, x) by the two halves of the
@@ -115,15 +110,6 @@ __device__ __forceinline__ uint2 pack_byte2(const uint32_t (&v)[8])
     o.y = __byte_perm(__byte_perm(v[4], v[5], 0x0062), __byte_perm(v[6], v[7], 0x0062), 0x5410);
     return o;
 }
-// the low mantissa bytes of eight MAGIC-biased floats as eight packed bytes
-__device__ __forceinline__ uint2 pack_magic_bytes(const float (&v)[8])
-{
-    uint2 o;
-    o.x = __byte_perm(__byte_perm(__float_as_uint(v[0]), __float_as_uint(v[1]), 0x0040), __byte_perm(__float_as_uint(v[2]), __float_as_uint(v[3]), 0x0040), 0x5410);
-    o.y = __byte_perm(__byte_perm(__float_as_uint(v[4]), __float_as_uint(v[5]), 0x0040), __byte_perm(__float_as_uint(v[6]), __float_as_uint(v[7]), 0x0040), 0x5410);
-    return o;
-}
-
 // Code size matters here: the L1.5 instruction cache holds 32 KiB, and the first version of this
 // kernel (Y transformed by its own copy of the code with immediate tables, both colour conversions
 // unrolled over the 8 rows: 5232 instructions = 84 KiB, executed once per thread) spent 5 of 6 issue
