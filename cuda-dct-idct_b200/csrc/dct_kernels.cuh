@@ -125,12 +125,11 @@ struct DirectParams {
     // f32 planes that are 32-byte aligned in address and pitch move with 256-bit accesses: bit 0 = the input plane
     // (all inputs of a batch), bit 1 = the output plane, bit 2 = the optional coefficient plane of a round trip
     int v8;
-    // early (fused round trips without coefficient plane only): the host has established that nothing this
-    // launch READS is written by the launch it may overlap with (see early loads, b200dct.cu): the block is
-    // loaded (L2-coherent loads) and transformed before griddepcontrol.wait, only the stores wait for the
-    // predecessor to complete -- CTAs of this launch work in the slots the predecessor's last wave leaves idle
-    // early = E > 0: the first E CTAs of the grid (one machine-full: later CTAs only start once these have
-    // left, i.e. after the predecessor completed) may take that path.
+    // early = E > 0 (fused round trips without coefficient plane only): the host has established that nothing
+    // this launch READS is written by the launch it may overlap with (see early loads, b200dct.cu).  The first
+    // E CTAs of the grid (one machine-full: later CTAs only start once these have left, i.e. after the
+    // predecessor completed) load their block (L2-coherent loads) and transform it before griddepcontrol.wait,
+    // only their stores wait for the predecessor to complete: they work in the slots its last wave leaves idle.
     int early;
     // completion counter of the (device, stream) record (b200dct.cu): chain_feed = F > 0: the last F CTAs of
     // the grid add 1 each at their end; a CTA takes the early path only if the counter still reads below
