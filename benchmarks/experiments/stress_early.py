@@ -23,8 +23,11 @@ def programme(seed, n_ops, kinds):
             ops.append(("copy", kind, a, b))
         elif r < 0.80:
             ops.append(("fill", kind, a, rnd.randrange(256)))
-        elif r < 0.90:
+        elif r < 0.86:
             ops.append(("add", kind, a, b))
+        elif r < 0.93 and kind in COEF:
+            c = rnd.randrange(NCOEF)
+            ops.append(("fwd", kind, a, c) if rnd.random() < 0.5 else ("inv", kind, c, b))   # the split API through coefficient planes
         else:
             ops.append(("batch", kind, a, b))
     return ops
@@ -35,8 +38,13 @@ SHAPE = {"u8": (8192, 8192, torch.uint8), "f32d": (4096, 4096, torch.float32), "
          "rgb": (4096, 4096, 3, torch.uint8), "anyf": (6001, 6007, torch.float32)}
 
 
+COEF = {"u8": torch.int16, "f32d": torch.float32, "f32t": torch.float32}   # coefficient plane dtype per kind
+NCOEF = 2
+
+
 def run(ops, sync, plans, init):
     bufs = {k: [t.clone() for t in init[k]] for k in init}
+    coefs = {k: [torch.zeros(SHAPE[k][:2], device="cuda", dtype=COEF[k]) for _ in range(NCOEF)] for k in COEF if k in init}
     s = torch.cuda.current_stream()
     for op in ops:
         kind = op[1]
@@ -58,6 +66,10 @@ def run(ops, sync, plans, init):
                 B[op[2]].bitwise_xor_(B[op[3]])
             else:
                 B[op[2]].add_(B[op[3]]).clamp_(0, 255).floor_()
+        elif op[0] == "fwd":
+            m.forward(B[op[2]], coef=coefs[kind][op[3]], plan=plans[kind])
+        elif op[0] == "inv":
+            m.inverse(coefs[kind][op[2]], img=B[op[3]], plan=plans[kind])
         elif op[0] == "batch":
             i, j = op[2], op[3]
             if i != j and kind not in ("rgb", "anyf"):
@@ -65,6 +77,8 @@ def run(ops, sync, plans, init):
         if sync:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
+    for k in coefs:
+        bufs[k] = bufs[k] + coefs[k]   # coefficient planes are compared as well
     return bufs
 
 

@@ -942,9 +942,12 @@ static int run(const b200dct_plan *pl, int mode, Plane in, Plane out, Plane coef
         }
         const unsigned long long ctas = (unsigned long long)grid.x * grid.y;
         const bool fills = per_sm > 0 && ctas > (unsigned long long)per_sm * (unsigned long long)di.sms;
-        const bool eligible = pdl && !capturing && mode == MODE_RT && !coef.ptr;
+        // the early path: fused round trips without a coefficient plane, forward calls without the X-128 write-back,
+        // inverse calls whose coefficients are a plane (not the zig-zag stream)
+        const bool eligible = pdl && !capturing && !coef.ptr && !shifted && !(mode == MODE_INV && in.dt == DT_I16ZZ);
         const Range rd = eligible ? plane_range(in.ptr, in.pitch, (size_t)W * elem_size(in.dt), H) : Range{};
-        const Range w0 = plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
+        const Range w0 = out.dt == DT_I16ZZ ? plane_range(out.ptr, out.pitch, (size_t)(W / 8) * 128, H / 8)
+                                            : plane_range(out.ptr, out.pitch, (size_t)W * elem_size(out.dt), H);
         const Range w1 = plane_range(coef.ptr, coef.pitch, coef_dt == DT_I16ZZ ? (size_t)(W / 8) * 128 : (size_t)W * elem_size(coef.dt),
                                      coef_dt == DT_I16ZZ ? H / 8 : H);
         const Range w2 = plane_range(shifted, in.pitch, (size_t)W * 4, H);

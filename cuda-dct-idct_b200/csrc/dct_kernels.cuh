@@ -125,7 +125,8 @@ struct DirectParams {
     // f32 planes that are 32-byte aligned in address and pitch move with 256-bit accesses: bit 0 = the input plane
     // (all inputs of a batch), bit 1 = the output plane, bit 2 = the optional coefficient plane of a round trip
     int v8;
-    // early = E > 0 (fused round trips without coefficient plane only): the host has established that nothing
+    // early = E > 0 (never with a coefficient plane beside a round trip, the X-128 write-back or a zig-zag input
+    // stream: every global write must be in the store section): the host has established that nothing
     // this launch READS is written by the launch it may overlap with (see early loads, b200dct.cu).  The first
     // E CTAs of the grid (one machine-full: later CTAs only start once these have left, i.e. after the
     // predecessor completed) load their block (L2-coherent loads) and transform it before griddepcontrol.wait,
@@ -307,14 +308,12 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     // programmatic dependent launch (no-ops unless the host asked for it): see k_tma
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     bool early = false;
-    if constexpr (MODE == MODE_RT) {
-        if (P.early != 0 && P.coef == nullptr &&
-            (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x < (unsigned)P.early) { // CTA-uniform
-            __shared__ int s_early;
-            if (threadIdx.x == 0 && threadIdx.y == 0) s_early = ld_counter(P.chain) < P.chain_target; // thread (0,0) is always valid
-            __syncthreads();
-            early = s_early != 0;
-        }
+    if (P.early != 0 && P.coef == nullptr && P.shifted == nullptr && // every global write of such a launch is in its store section
+        (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x < (unsigned)P.early) { // CTA-uniform
+        __shared__ int s_early;
+        if (threadIdx.x == 0 && threadIdx.y == 0) s_early = ld_counter(P.chain) < P.chain_target; // thread (0,0) is always valid
+        __syncthreads();
+        early = s_early != 0;
     }
     if (!early) asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -331,16 +330,19 @@ __global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) 
     if constexpr (MODE == MODE_INV) {
         const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch;
         if (P.coef_dt == DT_F32) {
-            if (P.v8 & 1) sfor<8>([&](auto r) { ld_row_f32_v8<false>(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+            if ((P.v8 & 1) && early) sfor<8>([&](auto r) { ld_row_f32_v8<true>(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+            else if (P.v8 & 1) sfor<8>([&](auto r) { ld_row_f32_v8<false>(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
+            else if (early) sfor<8>([&](auto r) { ld_row_f32_cg(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
             else sfor<8>([&](auto r) { ld_row_f32(src + IC(r) * P.in_pitch + (size_t)bxi * 32, p[IC(r)]); });
-        } else if (P.coef_dt == DT_I16ZZ) { // pitch = bytes per block-row of the stream
+        } else if (P.coef_dt == DT_I16ZZ) { // pitch = bytes per block-row of the stream (never on the early path)
             const char *row = (const char *)in_plane + (size_t)by * P.in_pitch;
             if (zz_coop) ld_warp_zigzag(row + (size_t)blockIdx.y * 4096, zz_buf, threadIdx.x, p);
             else ld_block_zigzag(row + (size_t)bxi * 128, p);
         } else {
-            sfor<8>([&](auto r) {
-                unpack_i16(__ldg(reinterpret_cast<const uint4 *>(src + IC(r) * P.in_pitch + (size_t)bxi * 16)), p[IC(r)]);
-            });
+            uint4 w[8];
+            if (early) sfor<8>([&](auto r) { w[IC(r)] = __ldcg(reinterpret_cast<const uint4 *>(src + IC(r) * P.in_pitch + (size_t)bxi * 16)); });
+            else sfor<8>([&](auto r) { w[IC(r)] = __ldg(reinterpret_cast<const uint4 *>(src + IC(r) * P.in_pitch + (size_t)bxi * 16)); });
+            sfor<8>([&](auto r) { unpack_i16(w[IC(r)], p[IC(r)]); });
         }
     } else if constexpr (PIX == DT_F32) {
         const char *src = (const char *)in_plane + (size_t)by * 8 * P.in_pitch + (size_t)bxi * 32;
