@@ -286,8 +286,11 @@ __device__ __forceinline__ void shift_row(float2 (&r)[4], float s)
 #ifndef B200DCT_DIRECT_MIN_BLOCKS
 #define B200DCT_DIRECT_MIN_BLOCKS 5
 #endif
+#ifndef B200DCT_METRICS_MIN_BLOCKS
+#define B200DCT_METRICS_MIN_BLOCKS 4
+#endif
 template <int MODE, int TK, int QMODE, int PIX, bool METRICS = false, bool FINV = false>
-__global__ void __launch_bounds__(128, METRICS ? 4 : B200DCT_DIRECT_MIN_BLOCKS) k_direct(const __grid_constant__ DirectParams P)
+__global__ void __launch_bounds__(128, METRICS ? B200DCT_METRICS_MIN_BLOCKS : B200DCT_DIRECT_MIN_BLOCKS) k_direct(const __grid_constant__ DirectParams P)
 {
     constexpr bool BIASED = inverse_is_biased(TK, FINV);
     // CTA = 32 block-columns x 4 block-rows; grid.x walks block-rows (no 65535 limit),
